@@ -1,0 +1,352 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/*.json.gz by running the UNMODIFIED reference engine.
+
+Runs only in the build container (imports ``/root/reference/src``; the GPU box
+has no reference tree).  The emitted fixtures pin the CPU oracle
+(tests/test_oracle_golden.py) and, through it and directly, the CUDA engine.
+
+    python oracle/make_golden.py            # writes every fixture
+
+Each fixture holds one graph (dense indices: node order = ``graph.nodes``
+insertion order, ghosts — edge endpoints without a node record — appended in
+first-seen order; edge order = ``graph.edges``) and the reference's answers
+for a battery of queries, all in index space.
+
+Known-answer graphs are rebuilt from the reference's own tests:
+  tests/test_graph_schema.py:328-386 (+ assertions :408-441, :895-946)
+  tests/test_dependency_reach.py:26-161
+  tests/test_graph_wave1.py:135-169 (impact_of / sources_of)
+  tests/test_graph_api.py:1585-1633 (derived path hops + edges)
+plus probes from SURVEY.md §8(a') and estates from the reference's generator
+(scripts/generate_graph_benchmark_estate.py) through the reference builder.
+"""
+
+from __future__ import annotations
+
+import gzip
+import importlib.util
+import json
+import random
+import sys
+from pathlib import Path
+
+REF = Path("/root/reference")
+sys.path.insert(0, str(REF / "src"))
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+
+from agent_bom.api.routes.graph import _derived_attack_paths  # noqa: E402
+from agent_bom.graph import (  # noqa: E402
+    EntityType,
+    RelationshipType,
+    UnifiedEdge,
+    UnifiedGraph,
+    UnifiedNode,
+    build_unified_graph_from_report,
+    compute_dependency_reach,
+)
+
+from agent_bom_b200.graph.schema import ENTITY_CODE, REL_CODE, REL_CODE_OTHER, enum_value  # noqa: E402
+
+OUT = ROOT / "tests" / "golden"
+
+AG, SRV, PKG, TOOL, VULN, CRED, MIS, PROV, USER = (
+    EntityType.AGENT, EntityType.SERVER, EntityType.PACKAGE, EntityType.TOOL, EntityType.VULNERABILITY,
+    EntityType.CREDENTIAL, EntityType.MISCONFIGURATION, EntityType.PROVIDER, EntityType.USER,
+)
+R = RelationshipType
+
+
+def mk(nodes, edges) -> UnifiedGraph:
+    """nodes: (id, type[, severity, risk_score[, label]]); edges: (src, dst, rel[, direction[, traversable]])."""
+    g = UnifiedGraph(scan_id="golden")
+    for n in nodes:
+        nid, et = n[0], n[1]
+        sev = n[2] if len(n) > 2 else ""
+        risk = n[3] if len(n) > 3 else 0.0
+        label = n[4] if len(n) > 4 else nid
+        g.add_node(UnifiedNode(id=nid, entity_type=et, label=label, severity=sev, risk_score=risk))
+    for e in edges:
+        g.add_edge(UnifiedEdge(source=e[0], target=e[1], relationship=e[2], direction=e[3] if len(e) > 3 else "directed",
+                               traversable=e[4] if len(e) > 4 else True))
+    return g
+
+
+# ── known-answer graphs ─────────────────────────────────────────────────────
+
+def kat_schema():  # tests/test_graph_schema.py:328-386
+    return mk(
+        [("agent:a", AG, "", 0, "agent-a"), ("agent:b", AG, "", 0, "agent-b"), ("server:a:fs", SRV, "", 0, "mcp-fs"),
+         ("server:b:fs", SRV, "", 0, "mcp-fs"), ("vuln:CVE-2024-1", VULN, "critical", 9.0, "CVE-2024-1"), ("cred:API_KEY", CRED, "", 0, "API_KEY")],
+        [("agent:a", "server:a:fs", R.USES), ("agent:b", "server:b:fs", R.USES), ("server:a:fs", "vuln:CVE-2024-1", R.VULNERABLE_TO),
+         ("server:a:fs", "cred:API_KEY", R.EXPOSES_CRED), ("agent:a", "agent:b", R.SHARES_SERVER, "bidirectional")],
+    )
+
+
+def kat_directed():  # tests/test_graph_schema.py:926-946
+    return mk([("a", AG), ("s", SRV), ("v", VULN)], [("a", "s", R.USES), ("s", "v", R.VULNERABLE_TO)])
+
+
+def kat_chain():  # tests/test_dependency_reach.py:26-83 (chain + second agent)
+    return mk(
+        [("agent:cursor", AG), ("server:mcp-fs", SRV), ("pkg:direct@1.0", PKG), ("pkg:transitive@2.0", PKG), ("vuln:CVE-2026-0001", VULN),
+         ("agent:claude", AG), ("server:other", SRV), ("vuln:CVE-2026-0002", VULN)],
+        [("agent:cursor", "server:mcp-fs", R.USES), ("server:mcp-fs", "pkg:direct@1.0", R.DEPENDS_ON), ("pkg:direct@1.0", "pkg:transitive@2.0", R.DEPENDS_ON),
+         ("pkg:transitive@2.0", "vuln:CVE-2026-0001", R.VULNERABLE_TO), ("agent:claude", "server:other", R.USES),
+         ("server:other", "pkg:transitive@2.0", R.DEPENDS_ON), ("pkg:direct@1.0", "vuln:CVE-2026-0002", R.VULNERABLE_TO)],
+    )
+
+
+def kat_reach_misc():  # tests/test_dependency_reach.py:86-161 (island, affects, dangling, lateral) in one graph
+    return mk(
+        [("agent:cursor", AG), ("pkg:orphan@1", PKG), ("vuln:CVE-2026-9999", VULN), ("server:mcp", SRV), ("pkg:p", PKG), ("vuln:CVE-2026-1234", VULN),
+         ("vuln:CVE-2026-0042", VULN), ("agent:a", AG), ("agent:b", AG), ("pkg:lateral@1", PKG)],
+        [("pkg:orphan@1", "vuln:CVE-2026-9999", R.VULNERABLE_TO), ("agent:cursor", "server:mcp", R.USES), ("server:mcp", "pkg:p", R.DEPENDS_ON),
+         ("vuln:CVE-2026-1234", "pkg:p", R.AFFECTS), ("agent:a", "agent:b", R.SHARES_SERVER), ("agent:b", "pkg:lateral@1", R.SHARES_SERVER)],
+    )
+
+
+def kat_derived():  # tests/test_graph_api.py:1585-1633 shape: agent -> server -> package -> vuln (+ creds/tools, server-level vuln, orphan)
+    return mk(
+        [("agent:a", AG), ("server:a:fs", SRV), ("pkg:npm:form-data", PKG), ("vuln:cve", VULN, "high", 0.0, "CVE-X"),
+         ("cred:TOKEN", CRED, "", 0, "TOKEN"), ("tool:read", TOOL, "", 0, "read"), ("tool:write", TOOL, "", 0, "write"),
+         ("user:u", USER), ("server:lonely", SRV), ("vuln:srv", VULN, "", 7.5, ""), ("mis:m", MIS, "low"), ("vuln:orphan", VULN, "critical")],
+        [("agent:a", "server:a:fs", R.USES), ("server:a:fs", "pkg:npm:form-data", R.DEPENDS_ON), ("pkg:npm:form-data", "vuln:cve", R.VULNERABLE_TO),
+         ("server:a:fs", "cred:TOKEN", R.EXPOSES_CRED), ("server:a:fs", "tool:read", R.PROVIDES_TOOL), ("server:a:fs", "tool:write", R.PROVIDES_TOOL),
+         ("user:u", "server:a:fs", R.USES), ("server:a:fs", "vuln:srv", R.VULNERABLE_TO), ("server:lonely", "vuln:srv", R.VULNERABLE_TO),
+         ("server:lonely", "pkg:npm:form-data", R.DEPENDS_ON), ("vuln:cve", "mis:m", R.TRIGGERS), ("server:a:fs", "mis:m", R.VULNERABLE_TO),
+         ("agent:a", "user:u", R.SHARES_CRED, "bidirectional"), ("server:a:fs", "agent:a", R.MANAGES)],
+    )
+
+
+def kat_probe():  # SURVEY §8(a'): order ties, non-traversable, bidirectional, ghost endpoint, self loop, dynamic rels
+    g = mk(
+        [("s", AG), ("b", SRV), ("a", SRV), ("c", PKG), ("d", VULN, "medium"), ("e", TOOL), ("f", CRED), ("z", AG)],
+        [("s", "b", R.USES), ("s", "a", R.USES), ("a", "c", R.DEPENDS_ON), ("b", "c", R.DEPENDS_ON), ("c", "d", R.VULNERABLE_TO, "directed", False),
+         ("a", "d", R.SHARES_CRED, "bidirectional"), ("d", "e", R.EXPLOITABLE_VIA), ("e", "e", R.ACCESSED), ("s", "e", R.INVOKED),
+         ("f", "f", R.SHARES_SERVER, "bidirectional"), ("z", "s", R.DELEGATED_TO), ("b", "ghost:1", R.CONTAINS), ("ghost:2", "c", R.CONTAINS),
+         ("e", "f", R.REACHES_TOOL, "bidirectional", False)],
+    )
+    return g
+
+
+def load_generator():
+    spec = importlib.util.spec_from_file_location("ref_gen", REF / "scripts" / "generate_graph_benchmark_estate.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def densify(report, c: int, b: int, v: int):
+    """Density post-processing probed in SURVEY.md §8(d) (only fields the builder reads)."""
+    for ai, agent in enumerate(report["agents"]):
+        for si, server in enumerate(agent["mcp_servers"]):
+            for ti, tool in enumerate(server["tools"]):
+                tool["capabilities"] = ["execute" if ti % 5 == 0 else "read"]
+            server["credential_env_vars"] = [f"TEAM{ai // b:05d}_TOKEN_{k}" for k in range(c)]
+            for pi, pkg in enumerate(server["packages"][:v]):
+                pkg["vulnerabilities"] = [{"id": f"CVE-2027-{ai:06d}{si:02d}{pi:02d}", "severity": ("critical", "high", "medium", "low")[(ai + pi) % 4]}]
+    return report
+
+
+def estate(agents: int, dense=None):
+    gen = load_generator()
+    report, _ = gen.generate_estate(agents=agents, seed=2145, vulnerable_package_rate=0.08)
+    if dense:
+        densify(report, *dense)
+    return build_unified_graph_from_report(report)
+
+
+def mesh_inventory():
+    """examples/agent-mesh-inventory.json + pinned blast-radius overlay."""
+    inv = json.loads((REF / "examples" / "agent-mesh-inventory.json").read_text())
+    rows = []
+    sev = ("critical", "high", "medium", "low")
+    k = 0
+    for agent in inv.get("agents", []):
+        for server in agent.get("mcp_servers", []):
+            for pkg in server.get("packages", []):
+                rows.append({
+                    "vulnerability_id": f"CVE-2030-{k:04d}", "severity": sev[k % 4], "package": pkg.get("name", ""),
+                    "package_name": pkg.get("name", ""), "package_version": pkg.get("version", ""), "ecosystem": pkg.get("ecosystem", ""),
+                    "risk_score": (k % 7) * 1.5,
+                })
+                k += 1
+    inv["blast_radius"] = rows
+    return build_unified_graph_from_report(inv)
+
+
+# ── extraction ──────────────────────────────────────────────────────────────
+
+class Indexer:
+    def __init__(self, g: UnifiedGraph):
+        self.ids = list(g.nodes.keys())
+        self.idx = {nid: i for i, nid in enumerate(self.ids)}
+        self.n_real = len(self.ids)
+        for e in g.edges:
+            for end in (e.source, e.target):
+                if end not in self.idx:
+                    self.idx[end] = len(self.ids)
+                    self.ids.append(end)
+
+    def __call__(self, nid):
+        return self.idx[nid]
+
+
+def graph_arrays(g: UnifiedGraph, ix: Indexer):
+    node_types = [ENTITY_CODE[enum_value(n.entity_type)] for n in g.nodes.values()] + [255] * (len(ix.ids) - ix.n_real)
+    edges = []
+    for e in g.edges:
+        flags = (1 if e.traversable else 0) | (2 if e.is_bidirectional else 0)
+        edges.append([ix(e.source), ix(e.target), REL_CODE.get(enum_value(e.relationship), REL_CODE_OTHER), flags])
+    # cross-check the adjacency model itself (a1): list order of adjacency / reverse_adjacency
+    adj = {ix(u): [[ix(e.target), REL_CODE.get(enum_value(e.relationship), REL_CODE_OTHER)] for e in lst] for u, lst in g.adjacency.items() if lst}
+    radj = {ix(u): [[ix(e.source), REL_CODE.get(enum_value(e.relationship), REL_CODE_OTHER)] for e in lst] for u, lst in g.reverse_adjacency.items() if lst}
+    return node_types, edges, adj, radj
+
+
+def run_battery(name: str, g: UnifiedGraph, rng: random.Random, small: bool, derived: bool = True):
+    ix = Indexer(g)
+    node_types, edges, adj, radj = graph_arrays(g, ix)
+    ids = ix.ids
+    real = ids[: ix.n_real]
+    findings = [n.id for n in g.nodes.values() if enum_value(n.entity_type) in ("vulnerability", "misconfiguration")]
+    agents = [n.id for n in g.nodes.values() if enum_value(n.entity_type) == "agent"]
+
+    def sample(pop, k):
+        pop = list(pop)
+        return pop if len(pop) <= k else rng.sample(pop, k)
+
+    cases: dict = {}
+
+    # impact_of
+    imp_sources = (real if small else findings + sample([r for r in real if r not in set(findings)], 300))
+    imp = []
+    for depth in ((4, 1, 2, 0) if small else (4, 2)):
+        for s in imp_sources:
+            r = g.impact_of(s, max_depth=depth)
+            imp.append({"s": ix(s), "d": depth, "nodes": sorted(ix(x) for x in r["affected_nodes"]), "by_type": r["affected_by_type"],
+                        "count": r["affected_count"], "maxd": r["max_depth_reached"]})
+    r = g.impact_of("no-such-node")
+    cases["impact_missing"] = r
+    cases["impact"] = imp
+
+    # bfs (ordered paths)
+    bfs_sources = real if small else agents + sample(findings, 50) + sample(real, 100)
+    bfs = []
+    for depth, trav in (((4, True), (2, True), (3, False), (0, True)) if small else ((4, True), (2, False))):
+        for s in bfs_sources:
+            bfs.append({"s": ix(s), "d": depth, "t": trav, "paths": [[ix(x) for x in p] for p in g.bfs(s, max_depth=depth, traversable_only=trav)]})
+    cases["bfs"] = bfs
+
+    # reachable_from
+    rf = []
+    for depth, trav, inc in (((6, False, True), (2, True, False), (1, False, True)) if small else ((6, False, True), (3, True, False))):
+        for s in (real if small else sample(real, 200) + agents[:50]):
+            rf.append({"s": ix(s), "d": depth, "t": trav, "inc": inc,
+                       "nodes": sorted(ix(x) for x in g.reachable_from(s, max_depth=depth, traversable_only=trav, include_source=inc))})
+    cases["reachable"] = rf
+
+    # shortest_path
+    sp = []
+    pairs = [(a, b) for a in real for b in real] if small else (
+        [(rng.choice(real), rng.choice(real)) for _ in range(300)] + [(rng.choice(agents), rng.choice(findings)) for _ in range(200) if agents and findings])
+    for a, b in pairs:
+        p = g.shortest_path(a, b)
+        sp.append({"a": ix(a), "b": ix(b), "path": None if p is None else [ix(x) for x in p]})
+    cases["shortest"] = sp
+
+    # traverse_subgraph
+    lateral = {R.SHARES_SERVER, R.SHARES_CRED, R.LATERAL_PATH}
+    reach4 = {R.USES, R.DEPENDS_ON, R.CONTAINS, R.PROVIDES_TOOL}
+    configs = []
+    for direction in ("forward", "reverse", "both"):
+        for kw in (
+            {}, {"traversable_only": True}, {"relationship_types": reach4}, {"relationship_types": lateral, "max_depth": 2},
+            {"static_only": True}, {"dynamic_only": True}, {"include_roots": False}, {"include_roots": False, "max_depth": 2},
+            {"max_nodes": 3}, {"max_edges": 4}, {"max_nodes": 7, "max_edges": 30, "max_depth": 6}, {"max_depth": 10, "max_nodes": 100000, "max_edges": 10**9},
+            {"max_depth": 0}, {"max_depth": 1, "max_nodes": 1},
+        ):
+            configs.append((direction, kw))
+    root_sets = []
+    pool = real
+    for _ in range(6 if small else 25):
+        root_sets.append([rng.choice(pool)])
+    for _ in range(4 if small else 10):
+        k = rng.randint(2, 4)
+        rs = [rng.choice(pool) for _ in range(k)]
+        root_sets.append(rs)
+    root_sets.append([pool[0], pool[0], "missing:root", pool[-1]])
+    if findings:
+        root_sets.append(findings[:3])
+    if len(ids) > ix.n_real:
+        root_sets.append([ids[ix.n_real]])  # ghost root: skipped by the reference
+    trav = []
+    for direction, kw in configs:
+        for rs in root_sets:
+            call = dict(direction=direction, max_depth=4, max_nodes=500, max_edges=10_000)
+            call.update(kw)
+            sub, depth_by, truncated = g.traverse_subgraph(list(rs), **call)
+            rec = {
+                "roots": [ix.idx.get(x, -1) for x in rs], "direction": direction,
+                "kw": {k: (sorted(REL_CODE[enum_value(r)] for r in v) if k == "relationship_types" else v) for k, v in kw.items()},
+                "nodes": sorted(ix(x) for x in sub.nodes), "depth": sorted([ix(k), v] for k, v in depth_by.items()), "truncated": truncated,
+                "edges": sorted([ix(e.source), ix(e.target), REL_CODE.get(enum_value(e.relationship), REL_CODE_OTHER)] for e in sub.edges),
+            }
+            trav.append(rec)
+    cases["traverse"] = trav
+
+    # compute_dependency_reach
+    rep = compute_dependency_reach(g)
+    cases["dependency_reach"] = {
+        "packages": [[ix(p.package_id), [ix(a) for a in p.reachable_from], p.min_hop_distance] for p in rep.packages.values()],
+        "vulnerabilities": [[ix(v.vulnerability_id), [ix(p) for p in v.package_ids], [ix(a) for a in v.reachable_from], v.min_hop_distance]
+                            for v in rep.vulnerabilities.values()],
+    }
+
+    # _derived_attack_paths (final, risk-sorted order)
+    if derived:
+        paths = _derived_attack_paths(g)
+        cases["derived_paths"] = [
+            {"hops": [ix(h) for h in p.hops], "edges": [REL_CODE[e] for e in p.edges], "risk": p.composite_risk,
+             "creds": p.credential_exposure, "tools": p.tool_exposure, "vuln_ids": p.vuln_ids, "source": ix(p.source), "target": ix(p.target)}
+            for p in paths
+        ]
+
+    doc = {
+        "name": name,
+        "n_real": ix.n_real,
+        "node_ids": ids,
+        "node_types": node_types,
+        "node_labels": [n.label for n in g.nodes.values()],
+        "node_risk": [float(n.risk_score or 0.0) for n in g.nodes.values()],
+        "node_severity": [n.severity for n in g.nodes.values()],
+        "edges": edges,
+        "adjacency": {str(k): v for k, v in adj.items()} if small else None,
+        "reverse_adjacency": {str(k): v for k, v in radj.items()} if small else None,
+        "findings": [ix(f) for f in findings],
+        "agents": [ix(a) for a in agents],
+        "cases": cases,
+    }
+    OUT.mkdir(parents=True, exist_ok=True)
+    path = OUT / f"{name}.json.gz"
+    with gzip.GzipFile(path, "wb", mtime=0) as fh:
+        fh.write(json.dumps(doc, separators=(",", ":"), sort_keys=True).encode())
+    print(f"{name}: {ix.n_real} nodes (+{len(ids) - ix.n_real} ghosts) {len(edges)} edges, {len(findings)} findings -> {path.name} {path.stat().st_size / 1024:.0f} KiB")
+
+
+def main():
+    rng = random.Random(20260921)
+    run_battery("kat_schema", kat_schema(), rng, small=True)
+    run_battery("kat_directed", kat_directed(), rng, small=True)
+    run_battery("kat_chain", kat_chain(), rng, small=True)
+    run_battery("kat_reach_misc", kat_reach_misc(), rng, small=True)
+    run_battery("kat_derived", kat_derived(), rng, small=True)
+    run_battery("kat_probe", kat_probe(), rng, small=True)
+    run_battery("mesh_inventory", mesh_inventory(), rng, small=False)
+    run_battery("estate_150", estate(150), rng, small=False)
+    run_battery("estate_dense_40", estate(40, dense=(6, 8, 3)), rng, small=False)
+
+
+if __name__ == "__main__":
+    main()
