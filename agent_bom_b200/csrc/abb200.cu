@@ -1,0 +1,742 @@
+// abb200.cu — C ABI of the B200 blast-radius engine: graph upload, walk dispatch,
+// exposure-path rows, dependency reach.  See include/abb200.h for the contract.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include <cub/cub.cuh>
+
+#include "../../include/abb200.h"
+#include "paths.cuh"
+#include "reach.cuh"
+#include "walk.cuh"
+
+using namespace abb;
+
+// ------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+
+static int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess) return fail(ABB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" const char *abb_last_error(void) { return g_err.c_str(); }
+extern "C" int abb_version(void) { return ABB_VERSION; }
+extern "C" int abb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+extern "C" int64_t abb_launch_count(void) { return g_launches.load(); }
+
+// ------------------------------------------------------------------ (a1) host CSR build
+extern "C" int64_t abb_csr_entries(int64_t n_edges, const uint8_t *flags) {
+    int64_t n = n_edges;
+    for (int64_t i = 0; i < n_edges; i++) n += (flags[i] & ABB_EDGE_BIDIRECTIONAL) ? 1 : 0;
+    return n;
+}
+
+extern "C" int abb_csr_build_host(int32_t n_nodes, int64_t n_edges, const int32_t *src, const int32_t *dst, const uint8_t *rel,
+                                  const uint8_t *flags, uint32_t *fwd_off, int32_t *fwd_nbr, uint8_t *fwd_meta, uint32_t *fwd_eid,
+                                  uint32_t *rev_off, int32_t *rev_nbr, uint8_t *rev_meta, uint32_t *rev_eid) {
+    if (n_nodes < 0 || n_edges < 0) return fail(ABB_ERR_ARG, "negative sizes");
+    if (n_edges >= (1ll << 31)) return fail(ABB_ERR_ARG, "edge index must fit 31 bits (eid2 is uint32)");
+    std::vector<uint64_t> fc(static_cast<size_t>(n_nodes) + 1, 0), rc(static_cast<size_t>(n_nodes) + 1, 0);
+    for (int64_t i = 0; i < n_edges; i++) {
+        int32_t s = src[i], d = dst[i];
+        if (s < 0 || s >= n_nodes || d < 0 || d >= n_nodes) return fail(ABB_ERR_ARG, "edge %lld endpoint out of range", (long long)i);
+        fc[s]++; rc[d]++;
+        if (flags[i] & ABB_EDGE_BIDIRECTIONAL) { fc[d]++; rc[s]++; }
+    }
+    uint64_t fa = 0, ra = 0;
+    for (int32_t u = 0; u < n_nodes; u++) {
+        uint64_t f = fc[u], r = rc[u];
+        fwd_off[u] = static_cast<uint32_t>(fa); rev_off[u] = static_cast<uint32_t>(ra);
+        fc[u] = fa; rc[u] = ra; fa += f; ra += r;
+    }
+    if (fa >= (1ull << 32)) return fail(ABB_ERR_ARG, "more than 2^32 adjacency entries");
+    fwd_off[n_nodes] = static_cast<uint32_t>(fa); rev_off[n_nodes] = static_cast<uint32_t>(ra);
+    // append in graph.edges order: adjacency[src] += e; reverse_adjacency[dst] += e;
+    // bidirectional: adjacency[dst] += rev(e); reverse_adjacency[src] += rev(e)   (container.py:174-198)
+    for (int64_t i = 0; i < n_edges; i++) {
+        int32_t s = src[i], d = dst[i];
+        uint8_t fl = flags[i];
+        uint8_t m = static_cast<uint8_t>((rel[i] & ABB_META_REL_MASK) | ((fl & ABB_EDGE_TRAVERSABLE) ? ABB_META_TRAVERSABLE : 0) |
+                                         ((fl & ABB_EDGE_BIDIRECTIONAL) ? ABB_META_BIDIRECTIONAL : 0));
+        uint32_t e2 = static_cast<uint32_t>(i) * 2u;
+        uint64_t p = fc[s]++; fwd_nbr[p] = d; fwd_meta[p] = m; fwd_eid[p] = e2;
+        uint64_t r = rc[d]++; rev_nbr[r] = s; rev_meta[r] = m; rev_eid[r] = e2;
+        if (fl & ABB_EDGE_BIDIRECTIONAL) {
+            uint8_t mr = static_cast<uint8_t>(m | ABB_META_REVERSED_COPY);
+            p = fc[d]++; fwd_nbr[p] = s; fwd_meta[p] = mr; fwd_eid[p] = e2 + 1;
+            r = rc[s]++; rev_nbr[r] = d; rev_meta[r] = mr; rev_eid[r] = e2 + 1;
+        }
+    }
+    return ABB_OK;
+}
+
+// ------------------------------------------------------------------ device buffers
+struct DevBuf {
+    void *p = nullptr; size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return ABB_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { e = cudaMalloc(&p, bytes); want = bytes; }
+        if (e != cudaSuccess) return fail(ABB_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        cap = want;
+        return ABB_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return static_cast<T *>(p); }
+};
+
+// pinned host blocks, recycled across results (cudaHostAlloc is milliseconds)
+struct PinnedPool {
+    std::mutex mu;
+    std::vector<std::pair<void *, size_t>> free_blocks;
+    void *get(size_t bytes, size_t *got) {
+        if (bytes == 0) bytes = 16;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            size_t best = SIZE_MAX, bi = SIZE_MAX;
+            for (size_t i = 0; i < free_blocks.size(); i++)
+                if (free_blocks[i].second >= bytes && free_blocks[i].second < best) { best = free_blocks[i].second; bi = i; }
+            if (bi != SIZE_MAX && best <= bytes * 4 + (1 << 20)) {
+                void *p = free_blocks[bi].first; *got = best;
+                free_blocks.erase(free_blocks.begin() + bi);
+                return p;
+            }
+        }
+        size_t want = bytes + bytes / 8;
+        void *p = nullptr;
+        if (cudaHostAlloc(&p, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        *got = want;
+        return p;
+    }
+    void put(void *p, size_t bytes) {
+        if (!p) return;
+        std::lock_guard<std::mutex> lk(mu);
+        if (free_blocks.size() >= 64) { cudaFreeHost(p); return; }
+        free_blocks.emplace_back(p, bytes);
+    }
+};
+static PinnedPool g_pinned;
+
+struct HostBlock {
+    void *p = nullptr; size_t bytes = 0;
+    bool alloc(size_t n) { p = g_pinned.get(n, &bytes); return p != nullptr; }
+    void release() { g_pinned.put(p, bytes); p = nullptr; bytes = 0; }
+    template <class T> T *as() const { return static_cast<T *>(p); }
+};
+
+// ------------------------------------------------------------------ graph handle
+struct abb_graph {
+    int device = 0;
+    bool owned = false;
+    GraphView v{};
+    int64_t bytes = 0;
+    int sm_count = 148;
+    std::mutex mu;                    // serialises use of the shared workspace
+    cudaStream_t stream = nullptr;    // host-API stream
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool walk_timed = false, paths_timed = false;
+    // tier bookkeeping
+    DevBuf ctl, ov1, ov2;
+    DevBuf g_bitmap, g_queue, g_par, g_dep;
+    int g_slots = 0; int64_t g_words = 0, g_qcap = 0;
+    DevBuf identity_rank;
+    // host-API staging
+    DevBuf d_roots, d_root_off, d_targets, d_qstart, d_qcount, d_qmaxd, d_qflags, d_qestart, d_qecount, d_qhist;
+    DevBuf d_nodes, d_parent, d_depth, d_edges, d_totals;
+    int64_t hint_nodes = 0, hint_edges = 0;
+    // paths staging
+    DevBuf p_findings, p_counts, p_off, p_hops, p_rels, p_ncred, p_ntool, p_scan_tmp;
+    int64_t hint_rows = 0;
+    // owned graph arrays
+    std::vector<void *> owned_ptrs;
+};
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+static int graph_finish_init(abb_graph *g) {
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, g->device));
+    g->sm_count = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
+    for (auto &e : g->ev) CUDA_TRY(cudaEventCreate(&e));
+    if (int rc = g->ctl.ensure(16 * sizeof(unsigned long long))) return rc;
+    // tier G scratch: a handful of per-warp slots, each able to hold a whole-graph traversal
+    const int64_t n = g->v.n;
+    g->g_words = (n + 31) / 32 + 1;
+    g->g_qcap = n + 4096;
+    const int64_t per_slot = g->g_words * 4 + g->g_qcap * 12;
+    int64_t slots = (2ll << 30) / std::max<int64_t>(per_slot, 1);
+    slots = std::max<int64_t>(4, std::min<int64_t>(64, slots));
+    slots = (slots / 4) * 4;
+    g->g_slots = static_cast<int>(slots);
+    if (int rc = g->g_bitmap.ensure(static_cast<size_t>(slots * g->g_words * 4))) return rc;
+    if (int rc = g->g_queue.ensure(static_cast<size_t>(slots * g->g_qcap * 4))) return rc;
+    if (int rc = g->g_par.ensure(static_cast<size_t>(slots * g->g_qcap * 4))) return rc;
+    if (int rc = g->g_dep.ensure(static_cast<size_t>(slots * g->g_qcap * 4))) return rc;
+    CUDA_TRY(cudaMemset(g->g_bitmap.p, 0, static_cast<size_t>(slots * g->g_words * 4)));
+    if (!g->v.rank) {
+        if (int rc = g->identity_rank.ensure(static_cast<size_t>(n + 1) * 4)) return rc;
+        std::vector<int32_t> id(static_cast<size_t>(n));
+        for (int64_t i = 0; i < n; i++) id[i] = static_cast<int32_t>(i);
+        CUDA_TRY(cudaMemcpy(g->identity_rank.p, id.data(), static_cast<size_t>(n) * 4, cudaMemcpyHostToDevice));
+        g->v.rank = g->identity_rank.as<int32_t>();
+    }
+    return ABB_OK;
+}
+
+static int check_csr(const abb_csr *c) {
+    if (!c) return fail(ABB_ERR_ARG, "null csr");
+    if (c->n_nodes < 0 || c->n_entries < 0) return fail(ABB_ERR_ARG, "negative sizes");
+    if (!c->fwd_off || !c->rev_off || !c->node_type) return fail(ABB_ERR_ARG, "missing csr arrays");
+    if (c->n_entries > 0 && (!c->fwd_nbr || !c->fwd_meta || !c->fwd_eid || !c->rev_nbr || !c->rev_meta || !c->rev_eid))
+        return fail(ABB_ERR_ARG, "missing csr entry arrays");
+    return ABB_OK;
+}
+
+static void view_from_csr(GraphView &v, const abb_csr *c) {
+    v.n = c->n_nodes; v.m = c->n_entries;
+    v.foff = c->fwd_off; v.fnbr = c->fwd_nbr; v.fmeta = c->fwd_meta; v.feid = c->fwd_eid;
+    v.roff = c->rev_off; v.rnbr = c->rev_nbr; v.rmeta = c->rev_meta; v.reid = c->rev_eid;
+    v.ntype = c->node_type; v.rank = c->node_rank;
+}
+
+extern "C" int abb_graph_upload(int device, const abb_csr *host, abb_graph **out) {
+    if (!out) return fail(ABB_ERR_ARG, "null out");
+    if (int rc = check_csr(host)) return rc;
+    if (abb_device_count() <= device || device < 0) return fail(ABB_ERR_CUDA, "no CUDA device %d (this library has no CPU fallback)", device);
+    DeviceGuard dg(device);
+    abb_graph *g = new abb_graph();
+    g->device = device; g->owned = true;
+    abb_csr d = *host;
+    const size_t n1 = static_cast<size_t>(host->n_nodes) + 1, m = static_cast<size_t>(host->n_entries);
+    auto up = [&](const void *src, size_t bytes, const void **dstp) -> int {
+        void *p = nullptr;
+        size_t alloc = bytes ? bytes : 16;
+        cudaError_t e = cudaMalloc(&p, alloc);
+        if (e != cudaSuccess) return fail(ABB_ERR_NOMEM, "cudaMalloc(%zu): %s", alloc, cudaGetErrorString(e));
+        g->owned_ptrs.push_back(p);
+        if (bytes) { e = cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice); if (e != cudaSuccess) return fail(ABB_ERR_CUDA, "H2D: %s", cudaGetErrorString(e)); }
+        g->bytes += static_cast<int64_t>(bytes);
+        *dstp = p;
+        return ABB_OK;
+    };
+    int rc = ABB_OK;
+#define UP(field, bytes) if (!rc) rc = up(host->field, (bytes), reinterpret_cast<const void **>(&d.field))
+    UP(fwd_off, n1 * 4); UP(fwd_nbr, m * 4); UP(fwd_meta, m); UP(fwd_eid, m * 4);
+    UP(rev_off, n1 * 4); UP(rev_nbr, m * 4); UP(rev_meta, m); UP(rev_eid, m * 4);
+    UP(node_type, n1 - 1);
+    if (host->node_rank) { UP(node_rank, (n1 - 1) * 4); }
+#undef UP
+    if (!rc) { view_from_csr(g->v, &d); rc = graph_finish_init(g); }
+    if (rc) { abb_graph_free(g); return rc; }
+    *out = g;
+    return ABB_OK;
+}
+
+extern "C" int abb_graph_adopt(int device, const abb_csr *dev, abb_graph **out) {
+    if (!out) return fail(ABB_ERR_ARG, "null out");
+    if (int rc = check_csr(dev)) return rc;
+    if (abb_device_count() <= device || device < 0) return fail(ABB_ERR_CUDA, "no CUDA device %d (this library has no CPU fallback)", device);
+    DeviceGuard dg(device);
+    abb_graph *g = new abb_graph();
+    g->device = device; g->owned = false;
+    view_from_csr(g->v, dev);
+    g->bytes = (static_cast<int64_t>(dev->n_nodes) + 1) * 8 + dev->n_entries * 18 + dev->n_nodes * 5;
+    int rc = graph_finish_init(g);
+    if (rc) { abb_graph_free(g); return rc; }
+    *out = g;
+    return ABB_OK;
+}
+
+extern "C" int abb_graph_view(const abb_graph *g, abb_csr *out) {
+    if (!g || !out) return fail(ABB_ERR_ARG, "null argument");
+    out->n_nodes = g->v.n; out->n_entries = g->v.m;
+    out->fwd_off = g->v.foff; out->fwd_nbr = g->v.fnbr; out->fwd_meta = g->v.fmeta; out->fwd_eid = g->v.feid;
+    out->rev_off = g->v.roff; out->rev_nbr = g->v.rnbr; out->rev_meta = g->v.rmeta; out->rev_eid = g->v.reid;
+    out->node_type = g->v.ntype; out->node_rank = g->v.rank;
+    return ABB_OK;
+}
+extern "C" int64_t abb_graph_bytes(const abb_graph *g) { return g ? g->bytes : 0; }
+extern "C" int abb_graph_device(const abb_graph *g) { return g ? g->device : -1; }
+
+extern "C" void abb_graph_free(abb_graph *g) {
+    if (!g) return;
+    DeviceGuard dg(g->device);
+    if (g->stream) { cudaStreamSynchronize(g->stream); cudaStreamDestroy(g->stream); }
+    for (auto &e : g->ev) if (e) cudaEventDestroy(e);
+    for (DevBuf *b : {&g->ctl, &g->ov1, &g->ov2, &g->g_bitmap, &g->g_queue, &g->g_par, &g->g_dep, &g->identity_rank, &g->d_roots, &g->d_root_off,
+                      &g->d_targets, &g->d_qstart, &g->d_qcount, &g->d_qmaxd, &g->d_qflags, &g->d_qestart, &g->d_qecount, &g->d_qhist, &g->d_nodes,
+                      &g->d_parent, &g->d_depth, &g->d_edges, &g->d_totals, &g->p_findings, &g->p_counts, &g->p_off, &g->p_hops, &g->p_rels,
+                      &g->p_ncred, &g->p_ntool, &g->p_scan_tmp})
+        b->release();
+    if (g->owned) for (void *p : g->owned_ptrs) cudaFree(p);
+    delete g;
+}
+
+// ------------------------------------------------------------------ walk specs (reference function -> spec)
+static abb_walk_spec spec_base() {
+    abb_walk_spec s; memset(&s, 0, sizeof s);
+    s.direction = ABB_DIR_FORWARD; s.max_depth = 4; s.rel_mask = 0xFFFFFFFFu; s.max_nodes = -1; s.max_edges = -1; s.emit_types = 0xFFFFFFFFu;
+    return s;
+}
+extern "C" abb_walk_spec abb_spec_impact_of(int32_t max_depth) {
+    abb_walk_spec s = spec_base();
+    s.direction = ABB_DIR_REVERSE; s.max_depth = max_depth < 0 ? 0 : max_depth;   // all relationships, traversable ignored
+    s.flags = ABB_WALK_MARK_ROOTS | ABB_WALK_OMIT_ROOTS | ABB_WALK_HIST | ABB_WALK_REAL_ROOTS;
+    return s;
+}
+extern "C" abb_walk_spec abb_spec_bfs(int32_t max_depth, int32_t traversable_only) {
+    abb_walk_spec s = spec_base();
+    // nodes at depth max_depth+1 are marked visited but never emitted (container.py:381-390): invisible, so walk to max_depth
+    s.max_depth = max_depth < 0 ? 0 : max_depth;
+    s.flags = ABB_WALK_MARK_ROOTS | ABB_WALK_OMIT_ROOTS | ABB_WALK_PARENTS | ABB_WALK_REAL_ROOTS | (traversable_only ? ABB_WALK_TRAVERSABLE_ONLY : 0);
+    return s;
+}
+extern "C" abb_walk_spec abb_spec_reachable_from(int32_t max_depth, int32_t traversable_only) {
+    abb_walk_spec s = spec_base();
+    s.max_depth = max_depth < 0 ? 0 : max_depth;
+    s.flags = ABB_WALK_MARK_ROOTS | ABB_WALK_OMIT_ROOTS | ABB_WALK_REAL_ROOTS | (traversable_only ? ABB_WALK_TRAVERSABLE_ONLY : 0);
+    return s;
+}
+extern "C" abb_walk_spec abb_spec_shortest_path(void) {
+    abb_walk_spec s = spec_base();
+    s.max_depth = -1;
+    s.flags = ABB_WALK_MARK_ROOTS | ABB_WALK_PARENTS | ABB_WALK_REAL_ROOTS | ABB_WALK_TARGET;
+    return s;
+}
+extern "C" abb_walk_spec abb_spec_traverse_subgraph(int32_t direction, int32_t max_depth, int64_t max_nodes, int64_t max_edges, int32_t traversable_only,
+                                                    uint32_t rel_mask, int32_t static_only, int32_t dynamic_only, int32_t include_roots) {
+    abb_walk_spec s = spec_base();
+    const uint32_t dyn = (1u << 26) | (1u << 27) | (1u << 28);   // invoked, accessed, delegated_to (container.py:777)
+    s.direction = direction; s.max_depth = max_depth < 0 ? 0 : max_depth;
+    s.max_nodes = max_nodes; s.max_edges = max_edges;
+    uint32_t m = rel_mask ? rel_mask : 0xFFFFFFFFu;
+    if (static_only) m &= ~dyn;
+    if (dynamic_only) m &= dyn;
+    s.rel_mask = m;
+    s.flags = ABB_WALK_DEPTHS | ABB_WALK_EDGES | ABB_WALK_REAL_ROOTS | (include_roots ? ABB_WALK_MARK_ROOTS : 0) | (traversable_only ? ABB_WALK_TRAVERSABLE_ONLY : 0);
+    return s;
+}
+extern "C" abb_walk_spec abb_spec_distances_along(uint32_t rel_mask, uint32_t emit_types) {
+    abb_walk_spec s = spec_base();
+    s.max_depth = -1; s.rel_mask = rel_mask;
+    s.flags = ABB_WALK_MARK_ROOTS | ABB_WALK_OMIT_ROOTS | ABB_WALK_DEPTHS;
+    s.emit_types = emit_types ? emit_types : 0xFFFFFFFFu;
+    return s;
+}
+
+// ------------------------------------------------------------------ walk dispatch
+constexpr int S1_H = 1024, S1_Q = 512, S1_WARPS = 8;
+constexpr int S2_H = 16384, S2_Q = 8192, S2_WARPS = 1;
+
+template <int H, int Q, int WARPS, bool PAR, bool META, bool BUD>
+static int launch_smem(const abb_graph *g, const WalkArgs &A, int64_t max_items, cudaStream_t st) {
+    auto kern = walk_smem_kernel<H, Q, PAR, META, BUD, WARPS>;
+    constexpr int stride = (SmemStore<H, Q, PAR>::kBytes + 15) & ~15;
+    const int smem = stride * WARPS;
+    static thread_local int occ_cache = -1;  // per instantiation
+    if (occ_cache < 0) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        int occ = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, smem));
+        occ_cache = std::max(1, occ);
+    }
+    int64_t grid = static_cast<int64_t>(g->sm_count) * occ_cache;
+    int64_t need = (max_items + static_cast<int64_t>(WARPS) * WORK_CHUNK - 1) / (static_cast<int64_t>(WARPS) * WORK_CHUNK);
+    grid = std::max<int64_t>(1, std::min(grid, need));
+    kern<<<static_cast<unsigned>(grid), WARPS * 32, smem, st>>>(A);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return ABB_OK;
+}
+
+template <int H, int Q, int WARPS>
+static int launch_smem_variant(const abb_graph *g, const WalkArgs &A, int64_t max_items, bool par, bool meta, bool bud, cudaStream_t st) {
+#define V(P, M, B) if (par == P && meta == M && bud == B) return launch_smem<H, Q, WARPS, P, M, B>(g, A, max_items, st)
+    V(false, false, false); V(false, false, true); V(false, true, false); V(false, true, true);
+    V(true, false, false); V(true, false, true); V(true, true, false); V(true, true, true);
+#undef V
+    return fail(ABB_ERR_ARG, "unreachable");
+}
+
+static int launch_global_variant(const abb_graph *g, const WalkArgs &A, bool meta, bool bud, cudaStream_t st) {
+    const int blocks = g->g_slots / 4;
+    if (meta && bud) walk_global_kernel<true, true><<<blocks, 128, 0, st>>>(A);
+    else if (meta) walk_global_kernel<true, false><<<blocks, 128, 0, st>>>(A);
+    else if (bud) walk_global_kernel<false, true><<<blocks, 128, 0, st>>>(A);
+    else walk_global_kernel<false, false><<<blocks, 128, 0, st>>>(A);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return ABB_OK;
+}
+
+// enqueue the three tiers; each later tier reads its work list + count from device memory
+static int enqueue_walk(abb_graph *g, const abb_walk_spec *spec, const abb_walk_io *io, cudaStream_t st) {
+    if (!spec || !io) return fail(ABB_ERR_ARG, "null spec/io");
+    if (io->n_queries < 0) return fail(ABB_ERR_ARG, "negative query count");
+    if (!(spec->direction & 3)) return fail(ABB_ERR_ARG, "direction must be forward, reverse or both");
+    if (io->n_queries >= (1ll << 31)) return fail(ABB_ERR_ARG, "too many queries in one batch");
+    const uint32_t fl = spec->flags;
+    if (!io->q_start || !io->q_count || !io->q_maxd || !io->q_flags || !io->totals || (!io->nodes && io->node_cap > 0))
+        return fail(ABB_ERR_ARG, "missing walk outputs");
+    if ((fl & ABB_WALK_PARENTS) && !io->parent) return fail(ABB_ERR_ARG, "PARENTS needs io.parent");
+    if ((fl & ABB_WALK_DEPTHS) && !io->depth) return fail(ABB_ERR_ARG, "DEPTHS needs io.depth");
+    if ((fl & ABB_WALK_EDGES) && (!io->q_estart || !io->q_ecount || (!io->edges && io->edge_cap > 0))) return fail(ABB_ERR_ARG, "EDGES needs edge outputs");
+    if ((fl & ABB_WALK_HIST) && !io->q_hist) return fail(ABB_ERR_ARG, "HIST needs io.q_hist");
+    if ((fl & ABB_WALK_TARGET) && !io->targets) return fail(ABB_ERR_ARG, "TARGET needs io.targets");
+    CUDA_TRY(cudaMemsetAsync(io->totals, 0, 2 * sizeof(unsigned long long), st));
+    if (io->n_queries == 0) return ABB_OK;
+    if (int rc = g->ov1.ensure(static_cast<size_t>(io->n_queries) * 4)) return rc;
+    if (int rc = g->ov2.ensure(static_cast<size_t>(io->n_queries) * 4)) return rc;
+    CUDA_TRY(cudaMemsetAsync(g->ctl.p, 0, 16 * sizeof(unsigned long long), st));
+    const bool par = fl & ABB_WALK_PARENTS;
+    const bool meta = spec->rel_mask != 0xFFFFFFFFu || (fl & ABB_WALK_TRAVERSABLE_ONLY);
+    const bool bud = spec->max_nodes >= 0 || spec->max_edges >= 0;
+    unsigned long long *ctl = g->ctl.as<unsigned long long>();
+    WalkArgs A{};
+    A.g = g->v; A.spec = *spec; A.io = *io;
+    // tier S1: every query
+    A.qlist = nullptr; A.nq = io->n_queries; A.nq_dev = nullptr; A.ctl = ctl; A.overflow = g->ov1.as<int32_t>();
+    if (int rc = launch_smem_variant<S1_H, S1_Q, S1_WARPS>(g, A, io->n_queries, par, meta, bud, st)) return rc;
+    // tier S2: queries that outgrew S1 (count = ctl[1])
+    A.qlist = g->ov1.as<int32_t>(); A.nq = 0; A.nq_dev = ctl + 1; A.ctl = ctl + 4; A.overflow = g->ov2.as<int32_t>();
+    if (int rc = launch_smem_variant<S2_H, S2_Q, S2_WARPS>(g, A, static_cast<int64_t>(g->sm_count) * 2 * WORK_CHUNK, par, meta, bud, st)) return rc;
+    // tier G: queries that outgrew S2 (count = ctl[5])
+    A.qlist = g->ov2.as<int32_t>(); A.nq = 0; A.nq_dev = ctl + 5; A.ctl = ctl + 8; A.overflow = nullptr;
+    A.g_bitmap = g->g_bitmap.as<uint32_t>(); A.g_queue = g->g_queue.as<int32_t>(); A.g_par = g->g_par.as<int32_t>(); A.g_dep = g->g_dep.as<int32_t>();
+    A.g_words = g->g_words; A.g_qcap = g->g_qcap;
+    return launch_global_variant(g, A, meta, bud, st);
+}
+
+extern "C" int abb_walk_launch(abb_graph *g, const abb_walk_spec *spec, const abb_walk_io *io, void *stream) {
+    if (!g) return fail(ABB_ERR_ARG, "null graph");
+    DeviceGuard dg(g->device);
+    std::lock_guard<std::mutex> lk(g->mu);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaEventRecord(g->ev[0], st));
+    int rc = enqueue_walk(g, spec, io, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(g->ev[1], st));
+    g->walk_timed = true;
+    return ABB_OK;
+}
+
+extern "C" float abb_last_walk_ms(abb_graph *g) {
+    if (!g || !g->walk_timed) return -1.f;
+    DeviceGuard dg(g->device);
+    float ms = -1.f;
+    if (cudaEventSynchronize(g->ev[1]) != cudaSuccess) return -1.f;
+    if (cudaEventElapsedTime(&ms, g->ev[0], g->ev[1]) != cudaSuccess) return -1.f;
+    return ms;
+}
+extern "C" float abb_last_paths_ms(abb_graph *g) {
+    if (!g || !g->paths_timed) return -1.f;
+    DeviceGuard dg(g->device);
+    float ms = -1.f;
+    if (cudaEventSynchronize(g->ev[3]) != cudaSuccess) return -1.f;
+    if (cudaEventElapsedTime(&ms, g->ev[2], g->ev[3]) != cudaSuccess) return -1.f;
+    return ms;
+}
+
+// ------------------------------------------------------------------ walk, host-buffer form
+struct abb_walk_result {
+    int64_t nq = 0, total_nodes = 0, total_edges = 0, h2d = 0, d2h = 0;
+    uint32_t flags = 0;
+    HostBlock q_start, q_count, q_maxd, q_flags, q_estart, q_ecount, q_hist, nodes, parent, depth, edges;
+};
+
+extern "C" void abb_walk_result_free(abb_walk_result *r) {
+    if (!r) return;
+    for (HostBlock *b : {&r->q_start, &r->q_count, &r->q_maxd, &r->q_flags, &r->q_estart, &r->q_ecount, &r->q_hist, &r->nodes, &r->parent, &r->depth, &r->edges})
+        b->release();
+    delete r;
+}
+extern "C" int64_t abb_walk_result_queries(const abb_walk_result *r) { return r->nq; }
+extern "C" int64_t abb_walk_result_total_nodes(const abb_walk_result *r) { return r->total_nodes; }
+extern "C" int64_t abb_walk_result_total_edges(const abb_walk_result *r) { return r->total_edges; }
+extern "C" const int64_t *abb_walk_result_start(const abb_walk_result *r) { return r->q_start.as<int64_t>(); }
+extern "C" const int32_t *abb_walk_result_count(const abb_walk_result *r) { return r->q_count.as<int32_t>(); }
+extern "C" const int32_t *abb_walk_result_maxd(const abb_walk_result *r) { return r->q_maxd.as<int32_t>(); }
+extern "C" const int32_t *abb_walk_result_flags(const abb_walk_result *r) { return r->q_flags.as<int32_t>(); }
+extern "C" const int64_t *abb_walk_result_estart(const abb_walk_result *r) { return r->q_estart.as<int64_t>(); }
+extern "C" const int64_t *abb_walk_result_ecount(const abb_walk_result *r) { return r->q_ecount.as<int64_t>(); }
+extern "C" const uint32_t *abb_walk_result_hist(const abb_walk_result *r) { return r->q_hist.as<uint32_t>(); }
+extern "C" const int32_t *abb_walk_result_nodes(const abb_walk_result *r) { return r->nodes.as<int32_t>(); }
+extern "C" const int32_t *abb_walk_result_parent(const abb_walk_result *r) { return r->parent.as<int32_t>(); }
+extern "C" const int32_t *abb_walk_result_depth(const abb_walk_result *r) { return r->depth.as<int32_t>(); }
+extern "C" const uint32_t *abb_walk_result_edges(const abb_walk_result *r) { return r->edges.as<uint32_t>(); }
+extern "C" int64_t abb_walk_result_h2d_bytes(const abb_walk_result *r) { return r->h2d; }
+extern "C" int64_t abb_walk_result_d2h_bytes(const abb_walk_result *r) { return r->d2h; }
+
+// stage inputs, run (re-run once if the arenas were too small), leave results on the device
+static int walk_device_stage(abb_graph *g, const abb_walk_spec *spec, const int32_t *roots, const int64_t *root_off, const int32_t *targets,
+                             int64_t nq, abb_walk_io *io_out, unsigned long long totals[2], int64_t *h2d) {
+    cudaStream_t st = g->stream;
+    const uint32_t fl = spec->flags;
+    const int64_t n_roots = root_off ? root_off[nq] : nq;
+    if (n_roots < 0) return fail(ABB_ERR_ARG, "bad root_off");
+    const size_t q1 = static_cast<size_t>(nq) + 1;
+    if (int rc = g->d_roots.ensure(static_cast<size_t>(n_roots + 1) * 4)) return rc;
+    if (root_off) if (int rc = g->d_root_off.ensure(q1 * 8)) return rc;
+    if (fl & ABB_WALK_TARGET) if (int rc = g->d_targets.ensure(q1 * 4)) return rc;
+    if (int rc = g->d_qstart.ensure(q1 * 8)) return rc;
+    if (int rc = g->d_qcount.ensure(q1 * 4)) return rc;
+    if (int rc = g->d_qmaxd.ensure(q1 * 4)) return rc;
+    if (int rc = g->d_qflags.ensure(q1 * 4)) return rc;
+    if (fl & ABB_WALK_EDGES) { if (int rc = g->d_qestart.ensure(q1 * 8)) return rc; if (int rc = g->d_qecount.ensure(q1 * 8)) return rc; }
+    if (fl & ABB_WALK_HIST) if (int rc = g->d_qhist.ensure(q1 * ABB_N_ENTITY_TYPES * 4)) return rc;
+    if (int rc = g->d_totals.ensure(2 * sizeof(unsigned long long))) return rc;
+    *h2d = 0;
+    if (n_roots) { CUDA_TRY(cudaMemcpyAsync(g->d_roots.p, roots, static_cast<size_t>(n_roots) * 4, cudaMemcpyHostToDevice, st)); *h2d += n_roots * 4; }
+    if (root_off) { CUDA_TRY(cudaMemcpyAsync(g->d_root_off.p, root_off, q1 * 8, cudaMemcpyHostToDevice, st)); *h2d += static_cast<int64_t>(q1) * 8; }
+    if (fl & ABB_WALK_TARGET) { CUDA_TRY(cudaMemcpyAsync(g->d_targets.p, targets, static_cast<size_t>(nq) * 4, cudaMemcpyHostToDevice, st)); *h2d += nq * 4; }
+
+    int64_t node_cap = std::max<int64_t>({g->hint_nodes, nq * 8, 1 << 16});
+    int64_t edge_cap = (fl & ABB_WALK_EDGES) ? std::max<int64_t>({g->hint_edges, nq * 16, 1 << 16}) : 0;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        if (int rc = g->d_nodes.ensure(static_cast<size_t>(node_cap) * 4)) return rc;
+        if (fl & ABB_WALK_PARENTS) if (int rc = g->d_parent.ensure(static_cast<size_t>(node_cap) * 4)) return rc;
+        if (fl & ABB_WALK_DEPTHS) if (int rc = g->d_depth.ensure(static_cast<size_t>(node_cap) * 4)) return rc;
+        if (fl & ABB_WALK_EDGES) if (int rc = g->d_edges.ensure(static_cast<size_t>(edge_cap) * 4)) return rc;
+        abb_walk_io io{};
+        io.n_queries = nq; io.roots = g->d_roots.as<int32_t>(); io.root_off = root_off ? g->d_root_off.as<int64_t>() : nullptr;
+        io.targets = (fl & ABB_WALK_TARGET) ? g->d_targets.as<int32_t>() : nullptr;
+        io.q_start = g->d_qstart.as<int64_t>(); io.q_count = g->d_qcount.as<int32_t>(); io.q_maxd = g->d_qmaxd.as<int32_t>(); io.q_flags = g->d_qflags.as<int32_t>();
+        io.q_estart = g->d_qestart.as<int64_t>(); io.q_ecount = g->d_qecount.as<int64_t>(); io.q_hist = g->d_qhist.as<uint32_t>();
+        io.nodes = g->d_nodes.as<int32_t>(); io.parent = g->d_parent.as<int32_t>(); io.depth = g->d_depth.as<int32_t>(); io.node_cap = node_cap;
+        io.edges = g->d_edges.as<uint32_t>(); io.edge_cap = edge_cap; io.totals = g->d_totals.as<unsigned long long>();
+        CUDA_TRY(cudaEventRecord(g->ev[0], st));
+        if (int rc = enqueue_walk(g, spec, &io, st)) return rc;
+        CUDA_TRY(cudaEventRecord(g->ev[1], st));
+        g->walk_timed = true;
+        CUDA_TRY(cudaMemcpyAsync(totals, g->d_totals.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        unsigned long long fatal = 0;
+        CUDA_TRY(cudaMemcpy(&fatal, g->ctl.as<unsigned long long>() + 10, sizeof fatal, cudaMemcpyDeviceToHost));
+        if (fatal) return fail(ABB_ERR_CAPACITY, "a traversal outgrew the global scratch tier (more than n_nodes+4096 queue entries)");
+        *io_out = io;
+        const bool fits = static_cast<int64_t>(totals[0]) <= node_cap && (!(fl & ABB_WALK_EDGES) || static_cast<int64_t>(totals[1]) <= edge_cap);
+        g->hint_nodes = std::max<int64_t>(g->hint_nodes, static_cast<int64_t>(totals[0]));
+        g->hint_edges = std::max<int64_t>(g->hint_edges, static_cast<int64_t>(totals[1]));
+        if (fits) return ABB_OK;
+        node_cap = std::max<int64_t>(node_cap, static_cast<int64_t>(totals[0]));
+        edge_cap = std::max<int64_t>(edge_cap, static_cast<int64_t>(totals[1]));
+    }
+    return fail(ABB_ERR_CAPACITY, "walk arenas still too small after resize");
+}
+
+static int walk_collect(abb_graph *g, const abb_walk_spec *spec, const abb_walk_io &io, const unsigned long long totals[2], int64_t h2d,
+                        abb_walk_result **out, bool sync) {
+    cudaStream_t st = g->stream;
+    const uint32_t fl = spec->flags;
+    const int64_t nq = io.n_queries;
+    abb_walk_result *r = new abb_walk_result();
+    r->nq = nq; r->flags = fl; r->total_nodes = static_cast<int64_t>(totals[0]); r->total_edges = (fl & ABB_WALK_EDGES) ? static_cast<int64_t>(totals[1]) : 0;
+    r->h2d = h2d;
+    const size_t q = static_cast<size_t>(nq), tn = static_cast<size_t>(r->total_nodes), te = static_cast<size_t>(r->total_edges);
+    bool ok = r->q_start.alloc(q * 8) && r->q_count.alloc(q * 4) && r->q_maxd.alloc(q * 4) && r->q_flags.alloc(q * 4) && r->nodes.alloc(tn * 4);
+    if (fl & ABB_WALK_EDGES) ok = ok && r->q_estart.alloc(q * 8) && r->q_ecount.alloc(q * 8) && r->edges.alloc(te * 4);
+    if (fl & ABB_WALK_HIST) ok = ok && r->q_hist.alloc(q * ABB_N_ENTITY_TYPES * 4);
+    if (fl & ABB_WALK_PARENTS) ok = ok && r->parent.alloc(tn * 4);
+    if (fl & ABB_WALK_DEPTHS) ok = ok && r->depth.alloc(tn * 4);
+    if (!ok) { abb_walk_result_free(r); return fail(ABB_ERR_NOMEM, "pinned host allocation failed"); }
+    auto d2h = [&](HostBlock &dst, const void *src, size_t bytes) -> cudaError_t {
+        r->d2h += static_cast<int64_t>(bytes);
+        return bytes ? cudaMemcpyAsync(dst.p, src, bytes, cudaMemcpyDeviceToHost, st) : cudaSuccess;
+    };
+    cudaError_t e = cudaSuccess;
+    auto acc = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+    acc(d2h(r->q_start, io.q_start, q * 8)); acc(d2h(r->q_count, io.q_count, q * 4)); acc(d2h(r->q_maxd, io.q_maxd, q * 4)); acc(d2h(r->q_flags, io.q_flags, q * 4));
+    acc(d2h(r->nodes, io.nodes, tn * 4));
+    if (fl & ABB_WALK_EDGES) { acc(d2h(r->q_estart, io.q_estart, q * 8)); acc(d2h(r->q_ecount, io.q_ecount, q * 8)); acc(d2h(r->edges, io.edges, te * 4)); }
+    if (fl & ABB_WALK_HIST) acc(d2h(r->q_hist, io.q_hist, q * ABB_N_ENTITY_TYPES * 4));
+    if (fl & ABB_WALK_PARENTS) acc(d2h(r->parent, io.parent, tn * 4));
+    if (fl & ABB_WALK_DEPTHS) acc(d2h(r->depth, io.depth, tn * 4));
+    if (e == cudaSuccess && sync) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { abb_walk_result_free(r); return fail(ABB_ERR_CUDA, "D2H failed: %s", cudaGetErrorString(e)); }
+    *out = r;
+    return ABB_OK;
+}
+
+extern "C" int abb_walk_host(abb_graph *g, const abb_walk_spec *spec, const int32_t *roots, const int64_t *root_off, const int32_t *targets,
+                             int64_t n_queries, abb_walk_result **out) {
+    if (!g || !spec || !out || n_queries < 0 || (n_queries > 0 && !roots)) return fail(ABB_ERR_ARG, "bad arguments");
+    if ((spec->flags & ABB_WALK_TARGET) && !targets) return fail(ABB_ERR_ARG, "TARGET needs targets");
+    DeviceGuard dg(g->device);
+    std::lock_guard<std::mutex> lk(g->mu);
+    abb_walk_io io{}; unsigned long long totals[2] = {0, 0}; int64_t h2d = 0;
+    if (int rc = walk_device_stage(g, spec, roots, root_off, targets, n_queries, &io, totals, &h2d)) return rc;
+    return walk_collect(g, spec, io, totals, h2d, out, true);
+}
+
+// ------------------------------------------------------------------ exposure-path rows
+static int enqueue_paths_count(abb_graph *g, const abb_paths_io *io, cudaStream_t st) {
+    if (!io || io->n_findings < 0 || !io->f_off || (io->n_findings && !io->findings)) return fail(ABB_ERR_ARG, "bad paths io");
+    const int64_t nf = io->n_findings;
+    if (int rc = g->p_counts.ensure(static_cast<size_t>(nf + 1) * 8)) return rc;
+    CUDA_TRY(cudaMemsetAsync(g->p_counts.p, 0, static_cast<size_t>(nf + 1) * 8, st));
+    if (nf) {
+        PathsArgs A{}; A.g = g->v; A.io = *io; A.counts = g->p_counts.as<int64_t>();
+        int64_t blocks = std::min<int64_t>((nf + 7) / 8, static_cast<int64_t>(g->sm_count) * 8);
+        paths_kernel<false><<<static_cast<unsigned>(std::max<int64_t>(1, blocks)), 256, 0, st>>>(A);
+        g_launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    size_t tmp = 0;
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp, g->p_counts.as<int64_t>(), io->f_off, static_cast<int>(nf + 1), st));
+    if (int rc = g->p_scan_tmp.ensure(tmp + 16)) return rc;
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(g->p_scan_tmp.p, tmp, g->p_counts.as<int64_t>(), io->f_off, static_cast<int>(nf + 1), st));
+    g_launches++;
+    return ABB_OK;
+}
+
+static int enqueue_paths_fill(abb_graph *g, const abb_paths_io *io, cudaStream_t st) {
+    if (!io || !io->f_off || !io->hops || !io->rels || !io->ncred || !io->ntool) return fail(ABB_ERR_ARG, "bad paths io");
+    if (!io->n_findings) return ABB_OK;
+    PathsArgs A{}; A.g = g->v; A.io = *io; A.counts = nullptr;
+    int64_t blocks = std::min<int64_t>((io->n_findings + 7) / 8, static_cast<int64_t>(g->sm_count) * 8);
+    paths_kernel<true><<<static_cast<unsigned>(std::max<int64_t>(1, blocks)), 256, 0, st>>>(A);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return ABB_OK;
+}
+
+extern "C" int abb_paths_count_launch(abb_graph *g, const abb_paths_io *io, void *stream) {
+    if (!g) return fail(ABB_ERR_ARG, "null graph");
+    DeviceGuard dg(g->device);
+    std::lock_guard<std::mutex> lk(g->mu);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaEventRecord(g->ev[2], st));
+    return enqueue_paths_count(g, io, st);
+}
+extern "C" int abb_paths_fill_launch(abb_graph *g, const abb_paths_io *io, void *stream) {
+    if (!g) return fail(ABB_ERR_ARG, "null graph");
+    DeviceGuard dg(g->device);
+    std::lock_guard<std::mutex> lk(g->mu);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = enqueue_paths_fill(g, io, st);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(g->ev[3], st));
+    g->paths_timed = true;
+    return ABB_OK;
+}
+
+struct abb_paths_result {
+    int64_t nf = 0, rows = 0, h2d = 0, d2h = 0;
+    HostBlock off, hops, rels, ncred, ntool;
+};
+extern "C" void abb_paths_result_free(abb_paths_result *r) {
+    if (!r) return;
+    for (HostBlock *b : {&r->off, &r->hops, &r->rels, &r->ncred, &r->ntool}) b->release();
+    delete r;
+}
+extern "C" int64_t abb_paths_result_rows(const abb_paths_result *r) { return r->rows; }
+extern "C" const int64_t *abb_paths_result_off(const abb_paths_result *r) { return r->off.as<int64_t>(); }
+extern "C" const int32_t *abb_paths_result_hops(const abb_paths_result *r) { return r->hops.as<int32_t>(); }
+extern "C" const int8_t *abb_paths_result_rels(const abb_paths_result *r) { return r->rels.as<int8_t>(); }
+extern "C" const int32_t *abb_paths_result_ncred(const abb_paths_result *r) { return r->ncred.as<int32_t>(); }
+extern "C" const int32_t *abb_paths_result_ntool(const abb_paths_result *r) { return r->ntool.as<int32_t>(); }
+extern "C" int64_t abb_paths_result_h2d_bytes(const abb_paths_result *r) { return r->h2d; }
+extern "C" int64_t abb_paths_result_d2h_bytes(const abb_paths_result *r) { return r->d2h; }
+
+// findings already on the device (d_findings) or staged from the host
+static int paths_run(abb_graph *g, const int32_t *h_findings, const int32_t *d_findings, int64_t nf, abb_paths_result **out) {
+    cudaStream_t st = g->stream;
+    abb_paths_result *r = new abb_paths_result();
+    r->nf = nf;
+    if (!d_findings) {
+        if (int rc = g->p_findings.ensure(static_cast<size_t>(nf + 1) * 4)) { delete r; return rc; }
+        if (nf) { CUDA_TRY(cudaMemcpyAsync(g->p_findings.p, h_findings, static_cast<size_t>(nf) * 4, cudaMemcpyHostToDevice, st)); r->h2d += nf * 4; }
+        d_findings = g->p_findings.as<int32_t>();
+    }
+    if (int rc = g->p_off.ensure(static_cast<size_t>(nf + 1) * 8)) { delete r; return rc; }
+    abb_paths_io io{};
+    io.n_findings = nf; io.findings = d_findings; io.f_off = g->p_off.as<int64_t>();
+    CUDA_TRY(cudaEventRecord(g->ev[2], st));
+    if (int rc = enqueue_paths_count(g, &io, st)) { delete r; return rc; }
+    int64_t total = 0;
+    CUDA_TRY(cudaMemcpyAsync(&total, io.f_off + nf, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    r->rows = total;
+    const size_t rows = static_cast<size_t>(total);
+    int rc = g->p_hops.ensure(rows * 16 + 16);
+    if (!rc) rc = g->p_rels.ensure(rows * 3 + 16);
+    if (!rc) rc = g->p_ncred.ensure(rows * 4 + 16);
+    if (!rc) rc = g->p_ntool.ensure(rows * 4 + 16);
+    if (rc) { delete r; return rc; }
+    io.hops = g->p_hops.as<int32_t>(); io.rels = g->p_rels.as<int8_t>(); io.ncred = g->p_ncred.as<int32_t>(); io.ntool = g->p_ntool.as<int32_t>(); io.row_cap = total;
+    rc = enqueue_paths_fill(g, &io, st);
+    if (rc) { delete r; return rc; }
+    CUDA_TRY(cudaEventRecord(g->ev[3], st));
+    g->paths_timed = true;
+    bool ok = r->off.alloc(static_cast<size_t>(nf + 1) * 8) && r->hops.alloc(rows * 16) && r->rels.alloc(rows * 3) && r->ncred.alloc(rows * 4) && r->ntool.alloc(rows * 4);
+    if (!ok) { abb_paths_result_free(r); return fail(ABB_ERR_NOMEM, "pinned host allocation failed"); }
+    cudaError_t e = cudaMemcpyAsync(r->off.p, io.f_off, static_cast<size_t>(nf + 1) * 8, cudaMemcpyDeviceToHost, st);
+    if (rows && e == cudaSuccess) e = cudaMemcpyAsync(r->hops.p, io.hops, rows * 16, cudaMemcpyDeviceToHost, st);
+    if (rows && e == cudaSuccess) e = cudaMemcpyAsync(r->rels.p, io.rels, rows * 3, cudaMemcpyDeviceToHost, st);
+    if (rows && e == cudaSuccess) e = cudaMemcpyAsync(r->ncred.p, io.ncred, rows * 4, cudaMemcpyDeviceToHost, st);
+    if (rows && e == cudaSuccess) e = cudaMemcpyAsync(r->ntool.p, io.ntool, rows * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { abb_paths_result_free(r); return fail(ABB_ERR_CUDA, "paths D2H failed: %s", cudaGetErrorString(e)); }
+    r->d2h = static_cast<int64_t>((nf + 1) * 8 + rows * 27);
+    *out = r;
+    return ABB_OK;
+}
+
+extern "C" int abb_paths_host(abb_graph *g, const int32_t *findings, int64_t n_findings, abb_paths_result **out) {
+    if (!g || !out || n_findings < 0 || (n_findings && !findings)) return fail(ABB_ERR_ARG, "bad arguments");
+    DeviceGuard dg(g->device);
+    std::lock_guard<std::mutex> lk(g->mu);
+    return paths_run(g, findings, nullptr, n_findings, out);
+}
+
+extern "C" int abb_exposure_host(abb_graph *g, const int32_t *findings, int64_t n_findings, int32_t max_depth, abb_walk_result **impact_out,
+                                 abb_paths_result **paths_out) {
+    if (!g || !impact_out || !paths_out || n_findings < 0 || (n_findings && !findings)) return fail(ABB_ERR_ARG, "bad arguments");
+    DeviceGuard dg(g->device);
+    std::lock_guard<std::mutex> lk(g->mu);
+    abb_walk_spec spec = abb_spec_impact_of(max_depth);
+    abb_walk_io io{}; unsigned long long totals[2] = {0, 0}; int64_t h2d = 0;
+    if (int rc = walk_device_stage(g, &spec, findings, nullptr, nullptr, n_findings, &io, totals, &h2d)) return rc;
+    // result copies of the walk are enqueued (not waited for) before the path kernels; the findings are already resident
+    abb_walk_result *wr = nullptr;
+    if (int rc = walk_collect(g, &spec, io, totals, h2d, &wr, false)) return rc;
+    abb_paths_result *pr = nullptr;
+    int rc = paths_run(g, nullptr, g->d_roots.as<int32_t>(), n_findings, &pr);
+    if (rc) { cudaStreamSynchronize(g->stream); abb_walk_result_free(wr); return rc; }
+    *impact_out = wr; *paths_out = pr;
+    return ABB_OK;
+}
+
+#include "reach_host.inl"

@@ -1,0 +1,451 @@
+// walk.cuh — batched, ordered, multi-source frontier BFS over the typed CSR (sm_100a).
+//
+// One warp owns one query at a time (persistent grid, atomic work counter).
+// The warp keeps the query's FIFO queue, visited set and per-entry depth in
+// shared memory (tier S) or, for the rare query that outgrows it, in a
+// per-warp global scratch slot with a bitmap visited set (tier G).
+//
+// Exactness: the reference engine is a sequential deque BFS
+// (graph/container.py:230-279,367-391,411-436,438-538; dependency_reach.py:169-198).
+// The warp reproduces its discovery ORDER, not only its sets:
+//   * a level's frontier is consumed in queue order, 32 frontier nodes at a time;
+//   * their adjacency rows are flattened (warp prefix sum over degrees) and the
+//     flattened candidate list is consumed 32 candidates at a time, i.e. in
+//     (queue position, row position) lexicographic order = the reference's scan order;
+//   * inside a 32-candidate chunk, __match_any_sync elects the lowest lane among
+//     duplicates of a neighbour and ballot/popc ranks give the append positions,
+//     so the queue grows exactly as the sequential loop would grow it;
+//   * max_edges / max_nodes budgets are applied with warp prefix counts at the
+//     exact candidate where the sequential loop would hit them.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/abb200.h"
+
+namespace abb {
+
+constexpr unsigned FULL = 0xFFFFFFFFu;
+constexpr int32_t EMPTY = -1;
+constexpr uint32_t NO_TOK = 0xFFFFu;
+
+struct GraphView {
+    int32_t n;
+    int64_t m;
+    const uint32_t *foff; const int32_t *fnbr; const uint8_t *fmeta; const uint32_t *feid;
+    const uint32_t *roff; const int32_t *rnbr; const uint8_t *rmeta; const uint32_t *reid;
+    const uint8_t *ntype;
+    const int32_t *rank;
+};
+
+struct WalkArgs {
+    GraphView g;
+    abb_walk_spec spec;
+    abb_walk_io io;
+    const int32_t *qlist;        // queries of this launch (NULL = 0..nq-1)
+    int64_t nq;
+    const unsigned long long *nq_dev;  // when set, the query count is read from device memory (overflow tiers)
+    unsigned long long *ctl;     // [0] work counter, [1] overflow count, [2] fatal flag
+    int32_t *overflow;           // query ids that outgrew this tier
+    // tier G scratch (per warp slot)
+    uint32_t *g_bitmap; int32_t *g_queue; int32_t *g_par; int32_t *g_dep;
+    int64_t g_words, g_qcap;
+};
+
+__device__ __forceinline__ unsigned lanemask_lt(int lane) { return (1u << lane) - 1u; }
+
+// ---------------------------------------------------------------- tier S store
+template <int H, int Q, bool PAR>
+struct SmemStore {
+    static constexpr bool kGlobal = false;
+    static constexpr int kBytes = H * 4 + Q * 4 + Q * 2 + Q + (PAR ? Q * 4 : 0);
+    int32_t *htab; int32_t *queue; int32_t *par; uint16_t *tok; uint8_t *dep;
+    __device__ SmemStore(unsigned char *base) {
+        htab = reinterpret_cast<int32_t *>(base);
+        queue = htab + H;
+        par = PAR ? queue + Q : nullptr;
+        tok = reinterpret_cast<uint16_t *>(queue + Q + (PAR ? Q : 0));
+        dep = reinterpret_cast<uint8_t *>(tok + Q);
+    }
+    __device__ void init(int lane) {
+        for (int i = lane; i < H; i += 32) htab[i] = EMPTY;
+        __syncwarp();
+    }
+    __device__ __forceinline__ int qcap() const { return Q; }
+    __device__ __forceinline__ int max_level() const { return 255; }
+    static_assert((H & (H - 1)) == 0 && Q * 2 <= H, "hash table must be a power of two and at most half full");
+    static constexpr int log2c(int v) { return v <= 1 ? 0 : 1 + log2c(v >> 1); }
+    __device__ __forceinline__ static uint32_t hash(int32_t k) { return (static_cast<uint32_t>(k) * 0x9E3779B1u) >> (32 - log2c(H)); }
+    __device__ __forceinline__ bool contains(int32_t k) const {
+        uint32_t h = hash(k);
+        for (;;) {
+            int32_t v = htab[h];
+            if (v == k) return true;
+            if (v == EMPTY) return false;
+            h = (h + 1) & (H - 1);
+        }
+    }
+    // true when newly inserted; slot token returned for O(1) clearing
+    __device__ __forceinline__ bool test_and_set(int32_t k, uint32_t &t) {
+        uint32_t h = hash(k);
+        for (;;) {
+            int32_t old = atomicCAS(&htab[h], EMPTY, k);
+            if (old == EMPTY) { t = h; return true; }
+            if (old == k) return false;
+            h = (h + 1) & (H - 1);
+        }
+    }
+    __device__ __forceinline__ int32_t q_get(int i) const { return queue[i]; }
+    __device__ __forceinline__ void put(int i, int32_t node, int32_t p, uint32_t t, int d) {
+        queue[i] = node; tok[i] = static_cast<uint16_t>(t); dep[i] = static_cast<uint8_t>(d);
+        if (PAR) par[i] = p;
+    }
+    __device__ __forceinline__ int32_t par_get(int i) const { return PAR ? par[i] : -1; }
+    __device__ __forceinline__ int dep_get(int i) const { return dep[i]; }
+    __device__ __forceinline__ void unset(int32_t, uint32_t t) { htab[t] = EMPTY; }
+    __device__ void clear(int count, int lane) {
+        __syncwarp();
+        for (int i = lane; i < count; i += 32) { uint32_t t = tok[i]; if (t != NO_TOK) htab[t] = EMPTY; }
+        __syncwarp();
+    }
+};
+
+// ---------------------------------------------------------------- tier G store
+struct GlobalStore {
+    static constexpr bool kGlobal = true;
+    uint32_t *bits; int32_t *queue; int32_t *par; int32_t *dep; int64_t cap;
+    __device__ void init(int) {}
+    __device__ __forceinline__ int64_t qcap() const { return cap; }
+    __device__ __forceinline__ int max_level() const { return 0x7FFFFFF0; }
+    __device__ __forceinline__ bool contains(int32_t k) const { return (bits[k >> 5] >> (k & 31)) & 1u; }
+    __device__ __forceinline__ bool test_and_set(int32_t k, uint32_t &t) {
+        t = 0;
+        uint32_t bit = 1u << (k & 31);
+        uint32_t old = atomicOr(&bits[k >> 5], bit);
+        return !(old & bit);
+    }
+    __device__ __forceinline__ int32_t q_get(int64_t i) const { return queue[i]; }
+    __device__ __forceinline__ void put(int64_t i, int32_t node, int32_t p, uint32_t, int d) {
+        queue[i] = node; dep[i] = d; if (par) par[i] = p;
+    }
+    __device__ __forceinline__ int32_t par_get(int64_t i) const { return par ? par[i] : -1; }
+    __device__ __forceinline__ int dep_get(int64_t i) const { return dep[i]; }
+    __device__ __forceinline__ void unset(int32_t k, uint32_t) { atomicAnd(&bits[k >> 5], ~(1u << (k & 31))); }
+    __device__ void clear(int64_t count, int lane) {
+        __syncwarp();
+        for (int64_t i = lane; i < count; i += 32) bits[queue[i] >> 5] = 0u;
+        __threadfence_block();
+        __syncwarp();
+    }
+};
+
+// ---------------------------------------------------------------- candidate enumeration
+// Flattened candidates of up to 32 frontier nodes.  Lane j describes frontier
+// node j: forward row [sF, sF+dF) then reverse row [sR, sR+dR).
+struct Frontier32 {
+    uint32_t sF, dF, sR, excl;  // excl = exclusive prefix of (dF+dR)
+    uint32_t total;
+};
+
+__device__ __forceinline__ Frontier32 load_frontier(const GraphView &g, int dir, int32_t u, bool valid) {
+    Frontier32 f; f.sF = f.dF = f.sR = 0; uint32_t dR = 0;
+    if (valid) {
+        if (dir & 1) { uint32_t a = __ldg(g.foff + u), b = __ldg(g.foff + u + 1); f.sF = a; f.dF = b - a; }
+        if (dir & 2) { uint32_t a = __ldg(g.roff + u), b = __ldg(g.roff + u + 1); f.sR = a; dR = b - a; }
+    }
+    uint32_t deg = f.dF + dR, inc = deg;
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) { uint32_t v = __shfl_up_sync(FULL, inc, s); if (lane >= s) inc += v; }
+    f.excl = inc - deg;
+    f.total = __shfl_sync(FULL, inc, 31);
+    return f;
+}
+
+struct Cand { int32_t nbr; uint32_t meta; uint32_t eid; int owner; bool active; };
+
+// candidate ci (clamped) -> owning frontier lane + CSR position
+template <bool NEED_META, bool NEED_EID>
+__device__ __forceinline__ Cand fetch_cand(const GraphView &g, const Frontier32 &f, uint32_t ci) {
+    Cand c; c.active = ci < f.total;
+    uint32_t cc = c.active ? ci : (f.total - 1);
+    int j = 0;
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        int t = j + s;
+        uint32_t v = __shfl_sync(FULL, f.excl, t & 31);
+        if (t < 32 && v <= cc) j = t;
+    }
+    // several lanes may share excl (zero-degree nodes): the LAST lane with excl<=cc owns it,
+    // but lanes past the frontier carry excl==total>cc, so j is a real frontier lane.
+    uint32_t ex = __shfl_sync(FULL, f.excl, j), sF = __shfl_sync(FULL, f.sF, j), dF = __shfl_sync(FULL, f.dF, j), sR = __shfl_sync(FULL, f.sR, j);
+    uint32_t k = cc - ex;
+    c.owner = j; c.meta = ABB_META_TRAVERSABLE; c.eid = 0; c.nbr = 0;
+    if (c.active) {
+        if (k < dF) {
+            uint32_t p = sF + k; c.nbr = __ldg(g.fnbr + p);
+            if (NEED_META) c.meta = __ldg(g.fmeta + p);
+            if (NEED_EID) c.eid = __ldg(g.feid + p);
+        } else {
+            uint32_t p = sR + (k - dF); c.nbr = __ldg(g.rnbr + p);
+            if (NEED_META) c.meta = __ldg(g.rmeta + p);
+            if (NEED_EID) c.eid = __ldg(g.reid + p);
+        }
+    }
+    return c;
+}
+
+__device__ __forceinline__ bool cand_passes(const abb_walk_spec &sp, const Cand &c) {
+    return c.active && ((sp.rel_mask >> (c.meta & ABB_META_REL_MASK)) & 1u) &&
+           (!(sp.flags & ABB_WALK_TRAVERSABLE_ONLY) || (c.meta & ABB_META_TRAVERSABLE));
+}
+
+__device__ __forceinline__ bool type_emitted(uint32_t emit_types, uint8_t t) {
+    return (emit_types >> (t < 31 ? t : 31)) & 1u;
+}
+
+// ---------------------------------------------------------------- one query
+// Returns false when the query outgrew the store (caller re-queues it for the next tier).
+template <class Store, bool NEED_META, bool BUDGET>
+__device__ bool walk_one(const WalkArgs &A, Store &st, int64_t q, int lane) {
+    const GraphView &g = A.g;
+    const abb_walk_spec &sp = A.spec;
+    const abb_walk_io &io = A.io;
+    const uint32_t fl = sp.flags;
+    using idx_t = decltype(st.qcap());
+
+    int64_t r0 = q, r1 = q + 1;
+    if (io.root_off) { r0 = io.root_off[q]; r1 = io.root_off[q + 1]; }
+
+    idx_t tail = 0;
+    long long nvis = 0;
+    // ---- seed the queue with the roots, in order (container.py:465-472)
+    for (int64_t rb = r0; rb < r1; rb += 32) {
+        int64_t ri = rb + lane;
+        int32_t r = ri < r1 ? __ldg(io.roots + ri) : -1;
+        bool ok = ri < r1 && r >= 0 && r < g.n;
+        if (ok && (fl & ABB_WALK_REAL_ROOTS) && __ldg(g.ntype + r) == ABB_NODE_GHOST) ok = false;
+        unsigned om = __ballot_sync(FULL, ok);
+        int cnt = __popc(om), rk = __popc(om & lanemask_lt(lane));
+        if (tail + cnt > st.qcap()) { st.clear(tail, lane); return false; }
+        uint32_t tok = NO_TOK;
+        if (fl & ABB_WALK_MARK_ROOTS) {
+            unsigned mm = __match_any_sync(FULL, ok ? r : (-2 - lane));
+            bool isnew = false;
+            if (ok && (__ffs(mm) - 1) == lane) isnew = st.test_and_set(r, tok);
+            nvis += __popc(__ballot_sync(FULL, isnew));
+        }
+        if (ok) st.put(tail + rk, r, -1, tok, 0);
+        tail += cnt;
+        __syncwarp();
+    }
+    const idx_t n_roots = tail;
+    int qflags = 0;
+    if (n_roots == 0) qflags |= ABB_QFLAG_NO_ROOT;
+    const int32_t target = (fl & ABB_WALK_TARGET) ? __ldg(io.targets + q) : -1;
+
+    idx_t lvl_begin = 0, lvl_end = tail, exp_end = 0;
+    int depth = 0, maxd = 0;
+    long long rec_edges = 0;      // passing candidates recorded (== edge_count while under budget)
+    bool stop = false;
+
+    while (lvl_begin < lvl_end && (sp.max_depth < 0 || depth < sp.max_depth) && !stop) {
+        if (depth + 1 > st.max_level()) { st.clear(tail, lane); return false; }
+        for (idx_t base = lvl_begin; base < lvl_end && !stop; base += 32) {
+            idx_t fi = base + lane;
+            bool fvalid = fi < lvl_end;
+            int32_t u = fvalid ? st.q_get(fi) : 0;
+            Frontier32 f = load_frontier(g, sp.direction, u, fvalid);
+            exp_end = (base + 32 < lvl_end) ? base + 32 : lvl_end;
+            for (uint32_t c0 = 0; c0 < f.total && !stop; c0 += 32) {
+                Cand c = fetch_cand<NEED_META, false>(g, f, c0 + lane);
+                bool pass = cand_passes(sp, c);
+                unsigned pm = __ballot_sync(FULL, pass);
+                if (BUDGET && sp.max_edges >= 0) {
+                    // edge_count += 1; if edge_count > max_edges: truncated, break  (container.py:507-510)
+                    long long my_ec = rec_edges + __popc(pm & (lanemask_lt(lane) | (1u << lane)));
+                    unsigned over = __ballot_sync(FULL, pass && my_ec > sp.max_edges);
+                    if (over) {
+                        int fo = __ffs(over) - 1;
+                        pass = pass && lane < fo;
+                        pm &= lanemask_lt(fo);
+                        qflags |= ABB_QFLAG_TRUNCATED;
+                        stop = true;
+                    }
+                }
+                rec_edges += __popc(pm);
+                // first lane among duplicates of a neighbour inside the chunk speaks for it
+                unsigned mm = __match_any_sync(FULL, pass ? c.nbr : (-2 - lane));
+                bool leader = pass && (__ffs(mm) - 1) == lane;
+                bool isnew = false;
+                uint32_t tok = NO_TOK;
+                if (BUDGET && sp.max_nodes >= 0) {
+                    // if neighbor in visited: continue; if len(visited) >= max_nodes: truncated; continue (container.py:515-519)
+                    bool unseen = leader && !st.contains(c.nbr);
+                    unsigned um = __ballot_sync(FULL, unseen);
+                    long long before = nvis + __popc(um & lanemask_lt(lane));
+                    bool allowed = unseen && before < sp.max_nodes;
+                    if (um && (nvis + __popc(um)) > sp.max_nodes) qflags |= ABB_QFLAG_TRUNCATED;
+                    // a non-leader duplicate of a denied neighbour is denied too (still unvisited, budget still full)
+                    if (allowed) isnew = st.test_and_set(c.nbr, tok);
+                } else if (leader) {
+                    isnew = st.test_and_set(c.nbr, tok);
+                }
+                unsigned nm = __ballot_sync(FULL, isnew);
+                int cnt = __popc(nm);
+                if (cnt) {
+                    if (tail + cnt > st.qcap()) {
+                        if (isnew) st.unset(c.nbr, tok);   // inserted this chunk but never queued
+                        st.clear(tail, lane);
+                        return false;
+                    }
+                    if (isnew) st.put(tail + __popc(nm & lanemask_lt(lane)), c.nbr, static_cast<int32_t>(base + c.owner), tok, depth + 1);
+                    tail += cnt; nvis += cnt;
+                    if ((fl & ABB_WALK_TARGET) && __any_sync(FULL, isnew && c.nbr == target)) { qflags |= ABB_QFLAG_TARGET_FOUND; stop = true; }
+                }
+                __syncwarp();
+            }
+        }
+        depth++;
+        lvl_begin = lvl_end; lvl_end = tail;
+        if (lvl_end > lvl_begin) maxd = depth;
+    }
+
+    // ---- emit the slice: reserve a contiguous range, then copy (optionally type-filtered)
+    const idx_t first = (fl & ABB_WALK_OMIT_ROOTS) ? n_roots : 0;
+    const bool filtered = sp.emit_types != 0xFFFFFFFFu;
+    long long count = static_cast<long long>(tail - first);
+    if (filtered) {
+        count = 0;
+        for (idx_t i = first; i < tail; i += 32) {
+            idx_t k = i + lane;
+            bool ok = k < tail && type_emitted(sp.emit_types, __ldg(g.ntype + st.q_get(k)));
+            count += __popc(__ballot_sync(FULL, ok));
+        }
+    }
+    unsigned long long start = 0;
+    if (lane == 0) start = atomicAdd(io.totals, static_cast<unsigned long long>(count));
+    start = __shfl_sync(FULL, start, 0);
+    const bool fits = static_cast<long long>(start) + count <= io.node_cap;
+    uint32_t hist_acc = 0;
+    if (fits || (fl & ABB_WALK_HIST)) {
+        unsigned long long w = start;
+        for (idx_t i = first; i < tail; i += 32) {
+            idx_t k = i + lane;
+            bool in = k < tail;
+            int32_t node = in ? st.q_get(k) : 0;
+            uint8_t t = 0;
+            if (in && (filtered || (fl & ABB_WALK_HIST))) t = __ldg(g.ntype + node);
+            bool ok = in && (!filtered || type_emitted(sp.emit_types, t));
+            unsigned okm = __ballot_sync(FULL, ok);
+            if (ok && fits) {
+                unsigned long long pos = w + __popc(okm & lanemask_lt(lane));
+                io.nodes[pos] = node;
+                if (fl & ABB_WALK_PARENTS) io.parent[pos] = st.par_get(k);
+                if (fl & ABB_WALK_DEPTHS) io.depth[pos] = st.dep_get(k);
+            }
+            w += __popc(okm);
+            if (fl & ABB_WALK_HIST) {
+                // roots are never counted (impact_of excludes the source, container.py:265)
+                bool hv = ok && k >= n_roots && t < ABB_N_ENTITY_TYPES;
+#pragma unroll
+                for (int b = 0; b < ABB_N_ENTITY_TYPES; b++) {
+                    unsigned bm = __ballot_sync(FULL, hv && t == b);
+                    if (lane == b) hist_acc += __popc(bm);
+                }
+            }
+        }
+    }
+    if ((fl & ABB_WALK_HIST) && lane < ABB_N_ENTITY_TYPES) io.q_hist[q * ABB_N_ENTITY_TYPES + lane] = hist_acc;
+
+    // ---- recorded edges: re-scan the expanded prefix in the same order (container.py:512-513)
+    unsigned long long estart = 0;
+    if (fl & ABB_WALK_EDGES) {
+        if (lane == 0) estart = atomicAdd(io.totals + 1, static_cast<unsigned long long>(rec_edges));
+        estart = __shfl_sync(FULL, estart, 0);
+        if (static_cast<long long>(estart) + rec_edges <= io.edge_cap) {
+            long long written = 0;
+            for (idx_t base = 0; base < exp_end && written < rec_edges; base += 32) {
+                idx_t fi = base + lane;
+                bool fvalid = fi < exp_end && (sp.max_depth < 0 || st.dep_get(fi) < sp.max_depth);
+                int32_t u = fvalid ? st.q_get(fi) : 0;
+                Frontier32 f = load_frontier(g, sp.direction, u, fvalid);
+                for (uint32_t c0 = 0; c0 < f.total && written < rec_edges; c0 += 32) {
+                    Cand c = fetch_cand<true, true>(g, f, c0 + lane);
+                    bool pass = cand_passes(sp, c);
+                    unsigned pm = __ballot_sync(FULL, pass);
+                    long long pos = written + __popc(pm & lanemask_lt(lane));
+                    if (pass && pos < rec_edges) io.edges[estart + pos] = c.eid;
+                    written += __popc(pm);
+                }
+            }
+        }
+    }
+
+    if (lane == 0) {
+        io.q_start[q] = static_cast<int64_t>(start);
+        io.q_count[q] = static_cast<int32_t>(count);
+        io.q_maxd[q] = maxd;
+        io.q_flags[q] = qflags;
+        if (fl & ABB_WALK_EDGES) { io.q_estart[q] = static_cast<int64_t>(estart); io.q_ecount[q] = rec_edges; }
+    }
+    st.clear(tail, lane);
+    return true;
+}
+
+constexpr int WORK_CHUNK = 4;
+
+__device__ __forceinline__ int64_t next_chunk(unsigned long long *ctl, int lane) {
+    unsigned long long v = 0;
+    if (lane == 0) v = atomicAdd(ctl, static_cast<unsigned long long>(WORK_CHUNK));
+    return static_cast<int64_t>(__shfl_sync(FULL, v, 0));
+}
+
+// ---------------------------------------------------------------- kernels
+template <int H, int Q, bool PAR, bool NEED_META, bool BUDGET, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) walk_smem_kernel(const WalkArgs A) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    using Store = SmemStore<H, Q, PAR>;
+    constexpr int kStride = (Store::kBytes + 15) & ~15;
+    Store st(smem + warp * kStride);
+    const int64_t nq = A.nq_dev ? static_cast<int64_t>(*A.nq_dev) : A.nq;
+    if (nq == 0) return;
+    st.init(lane);
+    for (;;) {
+        int64_t c = next_chunk(A.ctl, lane);
+        if (c >= nq) break;
+        int64_t ce = c + WORK_CHUNK < nq ? c + WORK_CHUNK : nq;
+        for (int64_t i = c; i < ce; i++) {
+            int64_t q = A.qlist ? A.qlist[i] : i;
+            if (!walk_one<Store, NEED_META, BUDGET>(A, st, q, lane)) {
+                if (lane == 0) { unsigned long long k = atomicAdd(A.ctl + 1, 1ull); A.overflow[k] = static_cast<int32_t>(q); }
+            }
+        }
+    }
+}
+
+template <bool NEED_META, bool BUDGET>
+__global__ void __launch_bounds__(128) walk_global_kernel(const WalkArgs A) {
+    const int lane = threadIdx.x & 31;
+    const int64_t slot = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    GlobalStore st;
+    st.bits = A.g_bitmap + slot * A.g_words;
+    st.queue = A.g_queue + slot * A.g_qcap;
+    st.par = A.g_par ? A.g_par + slot * A.g_qcap : nullptr;
+    st.dep = A.g_dep + slot * A.g_qcap;
+    st.cap = A.g_qcap;
+    const int64_t nq = A.nq_dev ? static_cast<int64_t>(*A.nq_dev) : A.nq;
+    for (;;) {
+        unsigned long long v = 0;
+        if (lane == 0) v = atomicAdd(A.ctl, 1ull);
+        int64_t i = static_cast<int64_t>(__shfl_sync(FULL, v, 0));
+        if (i >= nq) break;
+        int64_t q = A.qlist ? A.qlist[i] : i;
+        if (!walk_one<GlobalStore, NEED_META, BUDGET>(A, st, q, lane)) {
+            if (lane == 0) atomicExch(A.ctl + 2, 1ull);  // cannot happen unless scratch is undersized
+        }
+    }
+}
+
+}  // namespace abb

@@ -1,0 +1,302 @@
+"""DeviceGraph — a CSR resident in one B200's HBM plus the batched traversal calls on it.
+
+Thin Python face of the C ABI (include/abb200.h): every method stages its
+integer inputs, calls one ``abb_*_host`` entry point (H2D → sm_100a kernels →
+D2H inside the library) and wraps the pinned result arrays as numpy.  There is
+no CPU path: constructing a DeviceGraph without a CUDA device raises
+``EngineUnavailable``.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from .graph.csr import HostCSR
+from .graph.schema import ENTITY_VALUES, N_ENTITY_TYPES
+
+_vp = C.c_void_p
+
+
+def _view(ptr, n: int, dtype) -> np.ndarray:
+    """Copy ``n`` items from a C pointer into a fresh numpy array."""
+    if not ptr or n <= 0:
+        return np.zeros(max(n, 0), dtype=dtype)
+    nbytes = n * np.dtype(dtype).itemsize
+    buf = (C.c_char * nbytes).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype).copy()
+
+
+def _i32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+@dataclass
+class WalkResult:
+    """Ragged result of a batch of traversals.  Slice of query q = ``nodes[start[q] : start[q] + count[q]]``."""
+
+    start: np.ndarray
+    count: np.ndarray
+    maxd: np.ndarray
+    flags: np.ndarray
+    nodes: np.ndarray
+    parent: np.ndarray | None = None
+    depth: np.ndarray | None = None
+    hist: np.ndarray | None = None
+    estart: np.ndarray | None = None
+    ecount: np.ndarray | None = None
+    edges: np.ndarray | None = None
+    h2d_bytes: int = 0
+    d2h_bytes: int = 0
+    kernel_ms: float = 0.0
+
+    def __len__(self) -> int:
+        return int(self.count.shape[0])
+
+    def slice(self, q: int) -> np.ndarray:
+        s = int(self.start[q])
+        return self.nodes[s: s + int(self.count[q])]
+
+    def aux(self, q: int, which: str) -> np.ndarray:
+        s = int(self.start[q])
+        return getattr(self, which)[s: s + int(self.count[q])]
+
+    def edge_slice(self, q: int) -> np.ndarray:
+        s = int(self.estart[q])
+        return self.edges[s: s + int(self.ecount[q])]
+
+    def hist_dict(self, q: int) -> dict[str, int]:
+        return {ENTITY_VALUES[t]: int(c) for t, c in enumerate(self.hist[q]) if c}
+
+
+@dataclass
+class PathRows:
+    """Exposure-path rows in the reference's emission order (before risk ranking)."""
+
+    off: np.ndarray     # int64 [F+1] rows of finding i = [off[i], off[i+1])
+    hops: np.ndarray    # int32 [P,4] agent, server, vulnerable_source (-1 = the server), finding
+    rels: np.ndarray    # int8 [P,3]  relationship code per hop pair; -1 no edge; -2 n/a
+    ncred: np.ndarray
+    ntool: np.ndarray
+    h2d_bytes: int = 0
+    d2h_bytes: int = 0
+    kernel_ms: float = 0.0
+
+
+class DeviceGraph:
+    """Owns one ``abb_graph`` handle.  Thread-safe (the library serialises use of its workspace)."""
+
+    def __init__(self, handle: int, n_nodes: int, n_entries: int, device: int, keepalive=None):
+        self._h = _vp(handle)
+        self.n_nodes = n_nodes
+        self.n_entries = n_entries
+        self.device = device
+        self._keepalive = keepalive
+        self._lock = threading.Lock()
+
+    # ── construction ────────────────────────────────────────────────────
+    @classmethod
+    def upload(cls, csr: HostCSR, device: int = 0) -> "DeviceGraph":
+        lib = _lib.load()
+        _lib.require_device()
+        c = csr.c_struct()
+        h = _vp()
+        _lib.check(lib.abb_graph_upload(device, C.byref(c), C.byref(h)))
+        return cls(h.value, csr.n_nodes, csr.n_entries, device)
+
+    @classmethod
+    def adopt(cls, tensors: dict, n_nodes: int, n_entries: int, device: int) -> "DeviceGraph":
+        """Wrap device arrays owned by the caller (torch tensors, e.g. after an NCCL broadcast)."""
+        lib = _lib.load()
+        _lib.require_device()
+        c = _lib.Csr()
+        c.n_nodes, c.n_entries = n_nodes, n_entries
+        for name in ("fwd_off", "fwd_nbr", "fwd_meta", "fwd_eid", "rev_off", "rev_nbr", "rev_meta", "rev_eid", "node_type", "node_rank"):
+            t = tensors.get(name)
+            setattr(c, name, t.data_ptr() if t is not None else None)
+        h = _vp()
+        _lib.check(lib.abb_graph_adopt(device, C.byref(c), C.byref(h)))
+        return cls(h.value, n_nodes, n_entries, device, keepalive=tensors)
+
+    def close(self) -> None:
+        with self._lock:
+            if self._h:
+                _lib.load().abb_graph_free(self._h)
+                self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        if not self._h:
+            raise RuntimeError("DeviceGraph is closed")
+        return self._h
+
+    @property
+    def nbytes(self) -> int:
+        return int(_lib.load().abb_graph_bytes(self.handle))
+
+    # ── specs (reference function -> walk spec; the mapping lives in the C library) ──
+    @staticmethod
+    def spec_impact_of(max_depth: int = 4):
+        return _lib.load().abb_spec_impact_of(max_depth)
+
+    @staticmethod
+    def spec_bfs(max_depth: int = 4, traversable_only: bool = True):
+        return _lib.load().abb_spec_bfs(max_depth, int(traversable_only))
+
+    @staticmethod
+    def spec_reachable_from(max_depth: int = 6, traversable_only: bool = False):
+        return _lib.load().abb_spec_reachable_from(max_depth, int(traversable_only))
+
+    @staticmethod
+    def spec_shortest_path():
+        return _lib.load().abb_spec_shortest_path()
+
+    @staticmethod
+    def spec_traverse(direction: int, max_depth: int, max_nodes: int, max_edges: int, traversable_only: bool, rel_mask: int,
+                      static_only: bool, dynamic_only: bool, include_roots: bool):
+        return _lib.load().abb_spec_traverse_subgraph(direction, max_depth, max_nodes, max_edges, int(traversable_only), rel_mask & 0xFFFFFFFF,
+                                                      int(static_only), int(dynamic_only), int(include_roots))
+
+    @staticmethod
+    def spec_distances(rel_mask: int, emit_types: int = 0xFFFFFFFF):
+        return _lib.load().abb_spec_distances_along(rel_mask & 0xFFFFFFFF, emit_types & 0xFFFFFFFF)
+
+    # ── batched walk ────────────────────────────────────────────────────
+    def walk(self, spec, roots, root_off=None, targets=None) -> WalkResult:
+        lib = _lib.load()
+        roots = _i32(roots)
+        if root_off is not None:
+            root_off = np.ascontiguousarray(root_off, dtype=np.int64)
+            nq = int(root_off.shape[0]) - 1
+        else:
+            nq = int(roots.shape[0])
+        tg = _i32(targets) if targets is not None else None
+        res = _vp()
+        _lib.check(lib.abb_walk_host(self.handle, C.byref(spec), roots.ctypes.data, root_off.ctypes.data if root_off is not None else None,
+                                     tg.ctypes.data if tg is not None else None, nq, C.byref(res)))
+        try:
+            out = self._collect_walk(res, spec.flags)
+        finally:
+            lib.abb_walk_result_free(res)
+        out.kernel_ms = float(lib.abb_last_walk_ms(self.handle))
+        return out
+
+    @staticmethod
+    def _collect_walk(res, flags: int) -> WalkResult:
+        lib = _lib.load()
+        nq = int(lib.abb_walk_result_queries(res))
+        tn = int(lib.abb_walk_result_total_nodes(res))
+        te = int(lib.abb_walk_result_total_edges(res))
+        out = WalkResult(
+            start=_view(lib.abb_walk_result_start(res), nq, np.int64), count=_view(lib.abb_walk_result_count(res), nq, np.int32),
+            maxd=_view(lib.abb_walk_result_maxd(res), nq, np.int32), flags=_view(lib.abb_walk_result_flags(res), nq, np.int32),
+            nodes=_view(lib.abb_walk_result_nodes(res), tn, np.int32),
+            h2d_bytes=int(lib.abb_walk_result_h2d_bytes(res)), d2h_bytes=int(lib.abb_walk_result_d2h_bytes(res)),
+        )
+        if flags & _lib.WALK_PARENTS:
+            out.parent = _view(lib.abb_walk_result_parent(res), tn, np.int32)
+        if flags & _lib.WALK_DEPTHS:
+            out.depth = _view(lib.abb_walk_result_depth(res), tn, np.int32)
+        if flags & _lib.WALK_HIST:
+            out.hist = _view(lib.abb_walk_result_hist(res), nq * N_ENTITY_TYPES, np.uint32).reshape(nq, N_ENTITY_TYPES)
+        if flags & _lib.WALK_EDGES:
+            out.estart = _view(lib.abb_walk_result_estart(res), nq, np.int64)
+            out.ecount = _view(lib.abb_walk_result_ecount(res), nq, np.int64)
+            out.edges = _view(lib.abb_walk_result_edges(res), te, np.uint32)
+        return out
+
+    # convenience wrappers named after the reference functions
+    def impact_many(self, sources, max_depth: int = 4) -> WalkResult:
+        return self.walk(self.spec_impact_of(max_depth), sources)
+
+    def bfs_many(self, sources, max_depth: int = 4, traversable_only: bool = True) -> WalkResult:
+        return self.walk(self.spec_bfs(max_depth, traversable_only), sources)
+
+    def reachable_many(self, sources, max_depth: int = 6, traversable_only: bool = False) -> WalkResult:
+        return self.walk(self.spec_reachable_from(max_depth, traversable_only), sources)
+
+    def shortest_path_many(self, sources, targets) -> WalkResult:
+        return self.walk(self.spec_shortest_path(), sources, targets=targets)
+
+    # ── exposure-path rows ──────────────────────────────────────────────
+    @staticmethod
+    def _collect_paths(res, nf: int) -> PathRows:
+        lib = _lib.load()
+        rows = int(lib.abb_paths_result_rows(res))
+        return PathRows(
+            off=_view(lib.abb_paths_result_off(res), nf + 1, np.int64), hops=_view(lib.abb_paths_result_hops(res), rows * 4, np.int32).reshape(rows, 4),
+            rels=_view(lib.abb_paths_result_rels(res), rows * 3, np.int8).reshape(rows, 3), ncred=_view(lib.abb_paths_result_ncred(res), rows, np.int32),
+            ntool=_view(lib.abb_paths_result_ntool(res), rows, np.int32),
+            h2d_bytes=int(lib.abb_paths_result_h2d_bytes(res)), d2h_bytes=int(lib.abb_paths_result_d2h_bytes(res)),
+        )
+
+    def exposure_paths_many(self, findings) -> PathRows:
+        lib = _lib.load()
+        f = _i32(findings)
+        res = _vp()
+        _lib.check(lib.abb_paths_host(self.handle, f.ctypes.data, int(f.shape[0]), C.byref(res)))
+        try:
+            out = self._collect_paths(res, int(f.shape[0]))
+        finally:
+            lib.abb_paths_result_free(res)
+        out.kernel_ms = float(lib.abb_last_paths_ms(self.handle))
+        return out
+
+    def exposure_many(self, findings, max_depth: int = 4, collect: bool = True):
+        """One exposure traversal per finding: impact_of + derived exposure-path rows (BASELINE.json's unit of work)."""
+        lib = _lib.load()
+        f = _i32(findings)
+        wres, pres = _vp(), _vp()
+        _lib.check(lib.abb_exposure_host(self.handle, f.ctypes.data, int(f.shape[0]), max_depth, C.byref(wres), C.byref(pres)))
+        try:
+            if collect:
+                w = self._collect_walk(wres, _lib.WALK_HIST)
+                p = self._collect_paths(pres, int(f.shape[0]))
+            else:  # bench: results are already in pinned host memory; report sizes only
+                w = (int(lib.abb_walk_result_total_nodes(wres)), int(lib.abb_walk_result_h2d_bytes(wres)), int(lib.abb_walk_result_d2h_bytes(wres)))
+                p = (int(lib.abb_paths_result_rows(pres)), int(lib.abb_paths_result_h2d_bytes(pres)), int(lib.abb_paths_result_d2h_bytes(pres)))
+        finally:
+            lib.abb_walk_result_free(wres)
+            lib.abb_paths_result_free(pres)
+        return w, p
+
+    # ── dependency reach ────────────────────────────────────────────────
+    def dependency_reach(self, agents, rel_mask: int, vuln_pkg_mask: int) -> dict:
+        lib = _lib.load()
+        a = _i32(agents)
+        res = _vp()
+        _lib.check(lib.abb_dependency_reach_host(self.handle, a.ctypes.data, int(a.shape[0]), rel_mask & 0xFFFFFFFF, vuln_pkg_mask & 0xFFFFFFFF, C.byref(res)))
+        try:
+            npk = int(lib.abb_reach_n_packages(res))
+            nv = int(lib.abb_reach_n_vulns(res))
+            pkg_off = _view(lib.abb_reach_pkg_off(res), npk + 1, np.int64)
+            vpo = _view(lib.abb_reach_vuln_poff(res), nv + 1, np.int64)
+            vao = _view(lib.abb_reach_vuln_aoff(res), nv + 1, np.int64)
+            return dict(
+                pkg_ids=_view(lib.abb_reach_pkg_ids(res), npk, np.int32), pkg_off=pkg_off,
+                pkg_agents=_view(lib.abb_reach_pkg_agents(res), int(pkg_off[-1]) if npk else 0, np.int32),
+                pkg_minhop=_view(lib.abb_reach_pkg_minhop(res), npk, np.int32),
+                vuln_ids=_view(lib.abb_reach_vuln_ids(res), nv, np.int32), vuln_poff=vpo,
+                vuln_pkgs=_view(lib.abb_reach_vuln_pkgs(res), int(vpo[-1]) if nv else 0, np.int32), vuln_aoff=vao,
+                vuln_agents=_view(lib.abb_reach_vuln_agents(res), int(vao[-1]) if nv else 0, np.int32),
+                vuln_minhop=_view(lib.abb_reach_vuln_minhop(res), nv, np.int32),
+            )
+        finally:
+            lib.abb_reach_result_free(res)
+
+    # ── timing hooks used by bench.py ───────────────────────────────────
+    def last_walk_ms(self) -> float:
+        return float(_lib.load().abb_last_walk_ms(self.handle))
+
+    def last_paths_ms(self) -> float:
+        return float(_lib.load().abb_last_paths_ms(self.handle))

@@ -1,0 +1,299 @@
+/*
+ * abb200.h — C ABI of the B200 blast-radius engine (libabb200.so).
+ *
+ * This is the drop-in boundary for agent-bom's exposure-graph hot path: every
+ * entry point below replaces one reference interface (file:line under
+ * /root/reference/src/agent_bom/).  Plain pointers and sizes only — no torch,
+ * no C++ types.  INTEGRATION.md shows the ctypes binding a reference
+ * maintainer would add (the reference is pure Python, so the FFI is ctypes).
+ *
+ * Conventions
+ *   - every function returns ABB_OK (0) or a negative abb_status; the message
+ *     of the last failure on the calling thread is abb_last_error().
+ *   - "device" pointers are CUDA global-memory addresses on the graph's
+ *     device; "host" pointers are ordinary (ideally pinned) host memory.
+ *   - node ids are dense int32 indices (host keeps the string table); an id
+ *     that occurs only as an edge endpoint is a "ghost" (node_type 255).
+ *   - there is no CPU fallback anywhere in this library: without a CUDA
+ *     device every compute entry point fails with ABB_ERR_CUDA.
+ */
+#ifndef ABB200_H
+#define ABB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ABB_VERSION 100
+
+typedef enum abb_status {
+    ABB_OK = 0,
+    ABB_ERR_CUDA = -1,      /* CUDA runtime failure or no device */
+    ABB_ERR_ARG = -2,       /* invalid argument */
+    ABB_ERR_CAPACITY = -3,  /* caller-provided arena too small (needed sizes are reported) */
+    ABB_ERR_NOMEM = -4
+} abb_status;
+
+/* adjacency-entry meta byte (device format) */
+#define ABB_META_REL_MASK 0x1Fu
+#define ABB_META_TRAVERSABLE 0x20u
+#define ABB_META_BIDIRECTIONAL 0x40u
+#define ABB_META_REVERSED_COPY 0x80u
+/* per-edge input flags of the edge stream */
+#define ABB_EDGE_TRAVERSABLE 1u
+#define ABB_EDGE_BIDIRECTIONAL 2u
+
+#define ABB_NODE_GHOST 255u
+#define ABB_N_ENTITY_TYPES 24
+#define ABB_N_REL_TYPES 31
+
+const char *abb_last_error(void);
+int abb_version(void);
+int abb_device_count(void);
+
+/* ------------------------------------------------------------------------
+ * (a1) adjacency model — replaces UnifiedGraph.add_edge's adjacency /
+ * reverse_adjacency dict-of-lists (graph/container.py:97-101,146-198).
+ *
+ * Row u of the forward CSR is graph.adjacency[u] in list order, row u of the
+ * reverse CSR is graph.reverse_adjacency[u] in list order: original edge i
+ * (graph.edges order) contributes (row=src,nbr=dst,eid2=2i) forward and
+ * (row=dst,nbr=src,eid2=2i) reverse; a bidirectional edge also contributes
+ * its reversed copy (row=dst,nbr=src,eid2=2i+1) forward and
+ * (row=src,nbr=dst,eid2=2i+1) reverse.
+ * ---------------------------------------------------------------------- */
+typedef struct abb_csr {
+    int32_t n_nodes;          /* real nodes + ghosts */
+    int64_t n_entries;        /* entries per direction = n_edges + #bidirectional */
+    const uint32_t *fwd_off;  /* [n_nodes+1] */
+    const int32_t *fwd_nbr;   /* [n_entries] */
+    const uint8_t *fwd_meta;  /* [n_entries] */
+    const uint32_t *fwd_eid;  /* [n_entries] eid2 = 2*edge_index + reversed_copy */
+    const uint32_t *rev_off;
+    const int32_t *rev_nbr;
+    const uint8_t *rev_meta;
+    const uint32_t *rev_eid;
+    const uint8_t *node_type; /* [n_nodes] entity code, 255 = ghost */
+    const int32_t *node_rank; /* [n_nodes] rank of the id string among all ids (for sorted() outputs); may be NULL */
+} abb_csr;
+
+/* number of adjacency entries per direction for an edge stream */
+int64_t abb_csr_entries(int64_t n_edges, const uint8_t *flags);
+
+/* Host-side stable CSR build (counting sort, insertion order preserved).  All
+ * output arrays are caller-allocated: *_off[n_nodes+1], others [abb_csr_entries]. */
+int abb_csr_build_host(int32_t n_nodes, int64_t n_edges, const int32_t *src, const int32_t *dst, const uint8_t *rel,
+                       const uint8_t *flags, uint32_t *fwd_off, int32_t *fwd_nbr, uint8_t *fwd_meta, uint32_t *fwd_eid,
+                       uint32_t *rev_off, int32_t *rev_nbr, uint8_t *rev_meta, uint32_t *rev_eid);
+
+typedef struct abb_graph abb_graph; /* device-resident CSR pair + node types */
+
+/* copy a host CSR to `device` (library-owned device memory) */
+int abb_graph_upload(int device, const abb_csr *host, abb_graph **out);
+/* wrap device arrays owned by the caller (e.g. torch tensors filled by an NCCL broadcast) */
+int abb_graph_adopt(int device, const abb_csr *dev, abb_graph **out);
+/* device pointers of a graph (for broadcast / inspection) */
+int abb_graph_view(const abb_graph *g, abb_csr *out);
+int64_t abb_graph_bytes(const abb_graph *g);
+int abb_graph_device(const abb_graph *g);
+void abb_graph_free(abb_graph *g);
+
+/* ------------------------------------------------------------------------
+ * Batched ordered frontier BFS ("walk").  One spec covers every traversal of
+ * the reference engine; the abb_spec_* constructors below state the mapping.
+ *
+ * Semantics (identical to the reference's deque loops): FIFO queue seeded
+ * with the query's roots in order; a node is expanded only while
+ * depth < max_depth (max_depth < 0: unbounded); candidates of a node are its
+ * forward row (direction & 1) then its reverse row (direction & 2) in list
+ * order; a candidate passes iff its relationship bit is in rel_mask and
+ * (not TRAVERSABLE_ONLY or the entry is traversable); every passing candidate
+ * counts toward max_edges; an unvisited neighbour is appended (visited is
+ * marked at enqueue) unless max_nodes visited nodes already exist.  Output
+ * order == the reference's discovery order, parents == first-discoverer.
+ * ---------------------------------------------------------------------- */
+#define ABB_DIR_FORWARD 1
+#define ABB_DIR_REVERSE 2
+#define ABB_DIR_BOTH 3
+
+#define ABB_WALK_TRAVERSABLE_ONLY 0x001u /* skip non-traversable entries */
+#define ABB_WALK_MARK_ROOTS 0x002u       /* roots start visited (include_roots / single-source BFS) */
+#define ABB_WALK_OMIT_ROOTS 0x004u       /* do not emit the seeded root entries */
+#define ABB_WALK_PARENTS 0x008u          /* emit parent position (within the query's full queue, -1 for roots) */
+#define ABB_WALK_DEPTHS 0x010u           /* emit depth per emitted node */
+#define ABB_WALK_EDGES 0x020u            /* emit eid2 of every passing candidate in scan order */
+#define ABB_WALK_HIST 0x040u             /* per-query histogram of entity types over emitted non-root nodes */
+#define ABB_WALK_REAL_ROOTS 0x080u       /* roots that are ghosts / out of range are dropped (query flag bit1 if none left) */
+#define ABB_WALK_TARGET 0x100u           /* stop at first discovery of targets[q] (shortest_path) */
+
+#define ABB_QFLAG_TRUNCATED 1   /* a max_nodes / max_edges budget was hit */
+#define ABB_QFLAG_NO_ROOT 2     /* no valid root (reference returns its empty result) */
+#define ABB_QFLAG_TARGET_FOUND 4
+
+typedef struct abb_walk_spec {
+    int32_t direction;  /* ABB_DIR_* */
+    int32_t max_depth;  /* < 0: unbounded */
+    uint32_t rel_mask;  /* bit r set = relationship code r allowed (bit 31 = "other") */
+    uint32_t flags;     /* ABB_WALK_* */
+    int64_t max_nodes;  /* < 0: unbounded */
+    int64_t max_edges;  /* < 0: unbounded */
+    uint32_t emit_types;/* bit t set = emit nodes of entity code t; bit 31 = ghosts/other; 0xFFFFFFFF = all */
+    uint32_t reserved;
+} abb_walk_spec;
+
+/* UnifiedGraph.impact_of(node, max_depth) — graph/container.py:230-279 */
+abb_walk_spec abb_spec_impact_of(int32_t max_depth);
+/* UnifiedGraph.bfs(source, max_depth, traversable_only) — graph/container.py:367-391 */
+abb_walk_spec abb_spec_bfs(int32_t max_depth, int32_t traversable_only);
+/* UnifiedGraph.reachable_from(source, max_depth, traversable_only) — graph/container.py:411-436 */
+abb_walk_spec abb_spec_reachable_from(int32_t max_depth, int32_t traversable_only);
+/* UnifiedGraph.shortest_path(source, target) — graph/container.py:393-409 */
+abb_walk_spec abb_spec_shortest_path(void);
+/* UnifiedGraph.traverse_subgraph(...) — graph/container.py:438-538; rel_mask = relationship_types (0 = all) */
+abb_walk_spec abb_spec_traverse_subgraph(int32_t direction, int32_t max_depth, int64_t max_nodes, int64_t max_edges,
+                                         int32_t traversable_only, uint32_t rel_mask, int32_t static_only,
+                                         int32_t dynamic_only, int32_t include_roots);
+/* _bfs_distances_along(graph, start, allowed) — graph/dependency_reach.py:169-198 */
+abb_walk_spec abb_spec_distances_along(uint32_t rel_mask, uint32_t emit_types);
+
+/* Device-buffer form.  All pointers are device memory on the graph's device
+ * except where noted; optional outputs may be NULL when the matching flag is
+ * clear.  Results of query q occupy nodes[q_start[q] .. q_start[q]+q_count[q])
+ * (and edges[q_estart[q] .. +q_ecount[q])).  Slices are bump-allocated, so
+ * their order in the arena is unspecified; their contents are deterministic. */
+typedef struct abb_walk_io {
+    int64_t n_queries;
+    const int32_t *roots;     /* [root_off[n_queries]] or [n_queries] when root_off == NULL */
+    const int64_t *root_off;  /* NULL: query q has the single root roots[q] */
+    const int32_t *targets;   /* [n_queries], ABB_WALK_TARGET only */
+    int64_t *q_start;         /* [n_queries] */
+    int32_t *q_count;         /* [n_queries] */
+    int32_t *q_maxd;          /* [n_queries] max depth reached */
+    int32_t *q_flags;         /* [n_queries] ABB_QFLAG_* */
+    int64_t *q_estart;        /* [n_queries] (EDGES) */
+    int64_t *q_ecount;        /* [n_queries] (EDGES) recorded candidates */
+    uint32_t *q_hist;         /* [n_queries*24] (HIST) */
+    int32_t *nodes;           /* [node_cap] */
+    int32_t *parent;          /* [node_cap] (PARENTS) */
+    int32_t *depth;           /* [node_cap] (DEPTHS) */
+    int64_t node_cap;
+    uint32_t *edges;          /* [edge_cap] (EDGES) */
+    int64_t edge_cap;
+    unsigned long long *totals; /* device [2]: nodes / edges needed; zeroed by the launch */
+} abb_walk_io;
+
+/* Enqueue the walk on `stream` (a cudaStream_t, NULL = default stream).  Asynchronous. */
+int abb_walk_launch(abb_graph *g, const abb_walk_spec *spec, const abb_walk_io *io, void *stream);
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
+int64_t abb_launch_count(void);
+/* Timing hooks: elapsed milliseconds of the walk kernels of the most recent
+ * abb_walk_launch / *_host call on this graph (CUDA events on the launch stream;
+ * synchronises that stream). */
+float abb_last_walk_ms(abb_graph *g);
+float abb_last_paths_ms(abb_graph *g);
+
+/* Host-buffer form (the call the Python store makes): H2D of the roots, the
+ * walk, D2H of the results, arenas sized automatically.  The result owns
+ * pinned host arrays; accessors return pointers valid until abb_walk_result_free. */
+typedef struct abb_walk_result abb_walk_result;
+int abb_walk_host(abb_graph *g, const abb_walk_spec *spec, const int32_t *roots, const int64_t *root_off,
+                  const int32_t *targets, int64_t n_queries, abb_walk_result **out);
+int64_t abb_walk_result_queries(const abb_walk_result *r);
+int64_t abb_walk_result_total_nodes(const abb_walk_result *r);
+int64_t abb_walk_result_total_edges(const abb_walk_result *r);
+const int64_t *abb_walk_result_start(const abb_walk_result *r);
+const int32_t *abb_walk_result_count(const abb_walk_result *r);
+const int32_t *abb_walk_result_maxd(const abb_walk_result *r);
+const int32_t *abb_walk_result_flags(const abb_walk_result *r);
+const int64_t *abb_walk_result_estart(const abb_walk_result *r);
+const int64_t *abb_walk_result_ecount(const abb_walk_result *r);
+const uint32_t *abb_walk_result_hist(const abb_walk_result *r);
+const int32_t *abb_walk_result_nodes(const abb_walk_result *r);
+const int32_t *abb_walk_result_parent(const abb_walk_result *r);
+const int32_t *abb_walk_result_depth(const abb_walk_result *r);
+const uint32_t *abb_walk_result_edges(const abb_walk_result *r);
+int64_t abb_walk_result_h2d_bytes(const abb_walk_result *r);
+int64_t abb_walk_result_d2h_bytes(const abb_walk_result *r);
+void abb_walk_result_free(abb_walk_result *r);
+
+/* ------------------------------------------------------------------------
+ * Derived exposure paths — replaces _derived_attack_paths' topology walk
+ * (api/routes/graph.py:686-760) and _edge_relationships_for_hops (:488-503).
+ * One row per (agent, server, vulnerable_source, finding), in the reference's
+ * emission order (findings in the given order, in-edges in graph.edges order,
+ * agents sorted by node_rank).  Risk scoring and the final stable sort
+ * (:762-786) need Python floats and are done by the host layer.
+ *   hops [n_paths*4] : agent, server, vulnerable_source (-1 when it is the server), finding
+ *   rels [n_paths*3] : relationship code per consecutive hop pair; -1 = the pair
+ *                      has no edge (the reference skips it); -2 = not applicable
+ *   ncred/ntool      : EXPOSES_CRED / PROVIDES_TOOL out-edges of the server (un-deduplicated)
+ * ---------------------------------------------------------------------- */
+typedef struct abb_paths_io {
+    int64_t n_findings;
+    const int32_t *findings;  /* device [n_findings] */
+    int64_t *f_off;           /* device [n_findings+1] exclusive scan of per-finding path counts */
+    int32_t *hops;            /* device [row_cap*4] */
+    int8_t *rels;             /* device [row_cap*3] */
+    int32_t *ncred;           /* device [row_cap] */
+    int32_t *ntool;           /* device [row_cap] */
+    int64_t row_cap;
+} abb_paths_io;
+
+/* pass 1: per-finding counts + exclusive scan into f_off (f_off[n_findings] = total rows) */
+int abb_paths_count_launch(abb_graph *g, const abb_paths_io *io, void *stream);
+/* pass 2: fill rows (requires row_cap >= total) */
+int abb_paths_fill_launch(abb_graph *g, const abb_paths_io *io, void *stream);
+
+typedef struct abb_paths_result abb_paths_result;
+int abb_paths_host(abb_graph *g, const int32_t *findings, int64_t n_findings, abb_paths_result **out);
+int64_t abb_paths_result_rows(const abb_paths_result *r);
+const int64_t *abb_paths_result_off(const abb_paths_result *r); /* [n_findings+1] */
+const int32_t *abb_paths_result_hops(const abb_paths_result *r);
+const int8_t *abb_paths_result_rels(const abb_paths_result *r);
+const int32_t *abb_paths_result_ncred(const abb_paths_result *r);
+const int32_t *abb_paths_result_ntool(const abb_paths_result *r);
+int64_t abb_paths_result_h2d_bytes(const abb_paths_result *r);
+int64_t abb_paths_result_d2h_bytes(const abb_paths_result *r);
+void abb_paths_result_free(abb_paths_result *r);
+
+/* ------------------------------------------------------------------------
+ * One "exposure traversal" per finding = impact_of(f, max_depth) + f's derived
+ * exposure paths (the unit of BASELINE.json's metric).  Host-buffer form used
+ * by the store's batched API and by bench.py's e2e leg: both kernels are
+ * enqueued back to back and the result copies overlap.
+ * ---------------------------------------------------------------------- */
+int abb_exposure_host(abb_graph *g, const int32_t *findings, int64_t n_findings, int32_t max_depth,
+                      abb_walk_result **impact_out, abb_paths_result **paths_out);
+
+/* ------------------------------------------------------------------------
+ * compute_dependency_reach — graph/dependency_reach.py:109-220.
+ * Pass 1: walk from every agent along rel_mask (unbounded depth), keeping
+ * package nodes and hop counts.  Pass 2 (device sort/segment): per package the
+ * reaching agents sorted by node_rank + min hops; per vulnerability the
+ * attached packages (affects / vulnerable_to in either list), the union of
+ * their agents and the min of their mins.
+ * All outputs are host arrays owned by the result.
+ * ---------------------------------------------------------------------- */
+typedef struct abb_reach_result abb_reach_result;
+int abb_dependency_reach_host(abb_graph *g, const int32_t *agents, int64_t n_agents, uint32_t rel_mask,
+                              uint32_t vuln_pkg_mask, abb_reach_result **out);
+int64_t abb_reach_n_packages(const abb_reach_result *r);
+const int32_t *abb_reach_pkg_ids(const abb_reach_result *r);     /* package nodes in node order */
+const int64_t *abb_reach_pkg_off(const abb_reach_result *r);     /* [n_packages+1] */
+const int32_t *abb_reach_pkg_agents(const abb_reach_result *r);  /* agents sorted by node_rank */
+const int32_t *abb_reach_pkg_minhop(const abb_reach_result *r);  /* 0 when unreached */
+int64_t abb_reach_n_vulns(const abb_reach_result *r);
+const int32_t *abb_reach_vuln_ids(const abb_reach_result *r);
+const int64_t *abb_reach_vuln_poff(const abb_reach_result *r);
+const int32_t *abb_reach_vuln_pkgs(const abb_reach_result *r);   /* sorted by node_rank */
+const int64_t *abb_reach_vuln_aoff(const abb_reach_result *r);
+const int32_t *abb_reach_vuln_agents(const abb_reach_result *r); /* sorted by node_rank */
+const int32_t *abb_reach_vuln_minhop(const abb_reach_result *r);
+void abb_reach_result_free(abb_reach_result *r);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ABB200_H */
