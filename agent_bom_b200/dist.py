@@ -1,0 +1,133 @@
+"""Multi-GPU plumbing: one process per GPU, one-time NCCL broadcast of the shared CSR, contiguous source shards.
+
+The exposure graph is replicated (≈1.9 GB at 10 M nodes / 100 M edges, trivial
+next to 180 GB of HBM3e); finding sources are independent, so after the
+broadcast there is NO data-path collective — each rank traverses its own
+contiguous slice of the source list.  ``torch.distributed``
+(backend ``nccl`` on GPUs, ``gloo`` in the CPU tests) is only the transport.
+"""
+
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+CSR_FIELDS = ("fwd_off", "fwd_nbr", "fwd_meta", "fwd_eid", "rev_off", "rev_nbr", "rev_meta", "rev_eid", "node_type", "node_rank")
+_TORCH_DTYPE = {"fwd_off": torch.int32, "fwd_nbr": torch.int32, "fwd_meta": torch.uint8, "fwd_eid": torch.int32, "rev_off": torch.int32,
+                "rev_nbr": torch.int32, "rev_meta": torch.uint8, "rev_eid": torch.int32, "node_type": torch.uint8, "node_rank": torch.int32}
+
+
+@dataclass
+class RankInfo:
+    rank: int
+    world: int
+    local_rank: int
+
+
+def init_from_env(backend: str | None = None) -> RankInfo:
+    """Join the process group described by RANK / WORLD_SIZE / LOCAL_RANK / MASTER_* (torchrun); no-op for a single process."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29517")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return RankInfo(rank, world, local)
+
+
+def shard_bounds(n_items: int, world: int, rank: int) -> tuple[int, int]:
+    """Contiguous, balanced split: the first ``n_items % world`` ranks get one extra item."""
+    base, extra = divmod(int(n_items), int(world))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard(items, info: RankInfo):
+    lo, hi = shard_bounds(len(items), info.world, info.rank)
+    return items[lo:hi]
+
+
+def _as_tensor(name: str, arr: np.ndarray) -> torch.Tensor:
+    a = np.ascontiguousarray(arr)
+    if a.dtype == np.uint32:
+        a = a.view(np.int32)
+    return torch.from_numpy(a)
+
+
+def broadcast_csr(host_csr, info: RankInfo, device: torch.device | str) -> tuple[dict, int, int]:
+    """Rank 0 holds ``host_csr`` (others pass None); returns (device tensors, n_nodes, n_entries) on every rank.
+
+    Sizes travel first, then each array is broadcast once from rank 0's device
+    copy — over NVLink 5 / NVSwitch with the ``nccl`` backend.
+    """
+    device = torch.device(device)
+    meta = torch.zeros(2, dtype=torch.int64)
+    if info.rank == 0:
+        meta[0], meta[1] = host_csr.n_nodes, host_csr.n_entries
+    if info.world > 1:
+        m = meta.to(device) if device.type == "cuda" else meta
+        dist.broadcast(m, src=0)
+        meta = m.cpu()
+    n_nodes, n_entries = int(meta[0]), int(meta[1])
+    lengths = {"fwd_off": n_nodes + 1, "rev_off": n_nodes + 1, "node_type": n_nodes, "node_rank": n_nodes}
+    tensors = {}
+    for name in CSR_FIELDS:
+        length = lengths.get(name, n_entries)
+        if info.rank == 0:
+            t = _as_tensor(name, getattr(host_csr, name)).to(device, non_blocking=False)
+            assert t.numel() == length, (name, t.numel(), length)
+        else:
+            t = torch.empty(length, dtype=_TORCH_DTYPE[name], device=device)
+        if info.world > 1:
+            dist.broadcast(t, src=0)
+        tensors[name] = t
+    return tensors, n_nodes, n_entries
+
+
+def broadcast_array(arr: np.ndarray | None, info: RankInfo, device: torch.device | str, dtype=torch.int32) -> torch.Tensor:
+    """Broadcast a 1-D integer array (e.g. the finding-source list) from rank 0."""
+    device = torch.device(device)
+    n = torch.zeros(1, dtype=torch.int64)
+    if info.rank == 0:
+        n[0] = len(arr)
+    if info.world > 1:
+        nn = n.to(device) if device.type == "cuda" else n
+        dist.broadcast(nn, src=0)
+        n = nn.cpu()
+    if info.rank == 0:
+        t = torch.from_numpy(np.ascontiguousarray(arr)).to(dtype).to(device)
+    else:
+        t = torch.empty(int(n[0]), dtype=dtype, device=device)
+    if info.world > 1:
+        dist.broadcast(t, src=0)
+    return t
+
+
+def max_over_ranks(value: float, info: RankInfo, device: torch.device | str) -> float:
+    if info.world == 1:
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(value: float, info: RankInfo, device: torch.device | str) -> float:
+    if info.world == 1:
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def barrier(info: RankInfo) -> None:
+    if info.world > 1:
+        dist.barrier()

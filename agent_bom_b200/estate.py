@@ -276,7 +276,7 @@ def generate(agents: int, seed: int = 2145, knobs: Knobs = Knobs(), exact_rank: 
     has_v = pk_pi < n_vul[pk_srv]
     vul27_key = _mk(K_VULN27, (pk_ai << 11) | (pk_si << 5) | pk_pi)
 
-    # ---- timelines: positions of node mentions / edges inside the per-agent builder loop
+    # ---- node timeline: position of every node MENTION inside the per-agent builder loop
     srv_nodes = 1 + n_pkg + n_vul + n_tool + n_cred
     srv_edges = 1 + n_pkg + n_vul + n_tool + n_cred * (1 + n_tool)
     ag_nodes = 2 + np.bincount(srv_agent, weights=srv_nodes, minlength=A).astype(np.int64)
@@ -289,88 +289,122 @@ def generate(agents: int, seed: int = 2145, knobs: Knobs = Knobs(), exact_rank: 
     srv_ebase = ag_ebase[srv_agent] + 1 + (cs_e - cs_e[srv_first[srv_agent]])
     NM, EM = int(ag_nbase[-1]), int(ag_ebase[-1])
 
-    nkey = np.zeros(NM, dtype=np.int64)
-    ntyp = np.zeros(NM, dtype=np.uint8)
-    nsev = np.full(NM, -1, dtype=np.int8)
-    e_s = np.zeros(EM, dtype=np.int64); e_d = np.zeros(EM, dtype=np.int64); e_r = np.zeros(EM, dtype=np.uint8)
+    hv = np.flatnonzero(has_v)
+    ppos = 1 + pk_pi + np.minimum(pk_pi, n_vul[pk_srv])
+    tbase = 1 + n_pkg + n_vul
+    pos_prov, pos_agent, pos_srv = ag_nbase[:-1], ag_nbase[:-1] + 1, srv_nbase
+    pos_pkg = srv_nbase[pk_srv] + ppos
+    pos_v27 = pos_pkg[hv] + 1
+    pos_tool = srv_nbase[tl_srv] + tbase[tl_srv] + tl_ti
+    pos_cred = srv_nbase[cr_srv] + (tbase + n_tool)[cr_srv] + cr_k
 
-    def put_nodes(pos, keys, etype, sev=None):
-        nkey[pos] = keys; ntyp[pos] = etype
+    # first-wins merge (add_node): only providers, packages and credentials can be mentioned twice
+    is_first = np.ones(NM, dtype=bool)
+
+    def first_positions(keys: np.ndarray, pos: np.ndarray) -> np.ndarray:
+        """timeline position of the first mention of each key, per mention; later mentions are flagged as merged."""
+        order = np.argsort(pos, kind="stable")
+        _, first_idx, inv = np.unique(keys[order], return_index=True, return_inverse=True)
+        fp_sorted = pos[order][first_idx][inv]
+        fp = np.empty_like(pos)
+        fp[order] = fp_sorted
+        is_first[pos[fp != pos]] = False
+        return fp
+
+    fp_prov = first_positions(prov_key, pos_prov)
+    fp_pkg = first_positions(pkg_key, pos_pkg)
+    fp_cred = first_positions(cred_key, pos_cred) if Cn else pos_cred
+    node_of_pos = np.cumsum(is_first, dtype=np.int64) - 1           # node index of the mention at a first-occurrence position
+    N0 = int(node_of_pos[-1]) + 1 if NM else 0
+    ix_prov = node_of_pos[fp_prov].astype(np.int32); ix_agent = node_of_pos[pos_agent].astype(np.int32); ix_srv = node_of_pos[pos_srv].astype(np.int32)
+    ix_pkg = node_of_pos[fp_pkg].astype(np.int32); ix_v27 = node_of_pos[pos_v27].astype(np.int32)
+    ix_tool = node_of_pos[pos_tool].astype(np.int32); ix_cred = node_of_pos[fp_cred].astype(np.int32)
+
+    # ---- blast-radius rows (scaffold :136-155 -> builder.py:385-471): first instance of each package NAME that drew "vulnerable"
+    cand = np.flatnonzero(_u01(seed, 13, pidx) < kn.vulnerable_package_rate)
+    if cand.size:
+        _, first_idx = np.unique(name_key[cand], return_index=True)
+        rows = cand[np.sort(first_idx)]
+    else:
+        rows = cand
+    K = int(rows.shape[0])
+    ix_v26 = (N0 + np.arange(K, dtype=np.int64)).astype(np.int32)
+    N = N0 + K
+
+    node_key = np.empty(N, dtype=np.int64); node_type = np.empty(N, dtype=np.uint8); node_sev = np.full(N, -1, dtype=np.int8)
+
+    def set_nodes(ix, keys, etype, sev=None):
+        node_key[ix] = keys; node_type[ix] = etype
         if sev is not None:
-            nsev[pos] = sev
+            node_sev[ix] = sev
+
+    sev27 = ((pk_ai + pk_pi) % 4).astype(np.int8)
+    set_nodes(ix_prov, prov_key, ET["provider"]); set_nodes(ix_agent, agent_key, ET["agent"]); set_nodes(ix_srv, srv_key, ET["server"])
+    set_nodes(ix_pkg, pkg_key, ET["package"]); set_nodes(ix_v27, vul27_key[hv], ET["vulnerability"], sev27[hv])
+    set_nodes(ix_tool, tool_key, ET["tool"]); set_nodes(ix_cred, cred_key, ET["credential"])
+    set_nodes(ix_v26, _mk(K_VULN26, np.arange(K, dtype=np.int64)), ET["vulnerability"], ((pk_ai[rows] + pk_pi[rows]) % 4).astype(np.int8))
+
+    # ---- edge timeline of the per-agent loop, written straight in node-index space
+    e_s = np.zeros(EM, dtype=np.int32); e_d = np.zeros(EM, dtype=np.int32); e_r = np.zeros(EM, dtype=np.uint8)
+    keep = np.ones(EM, dtype=bool)
 
     def put_edges(pos, s, d, r):
         e_s[pos] = s; e_d[pos] = d; e_r[pos] = r
 
-    put_nodes(ag_nbase[:-1], prov_key, ET["provider"])
-    put_nodes(ag_nbase[:-1] + 1, agent_key, ET["agent"])
-    put_edges(ag_ebase[:-1], prov_key, agent_key, R["hosts"])
-    put_nodes(srv_nbase, srv_key, ET["server"])
-    put_edges(srv_ebase, agent_key[srv_agent], srv_key, R["uses"])
-    ppos = 1 + pk_pi + np.minimum(pk_pi, n_vul[pk_srv])
-    put_nodes(srv_nbase[pk_srv] + ppos, pkg_key, ET["package"])
-    put_edges(srv_ebase[pk_srv] + ppos, srv_key[pk_srv], pkg_key, R["depends_on"])
-    hv = np.flatnonzero(has_v)
-    sev27 = ((pk_ai + pk_pi) % 4).astype(np.int8)
-    put_nodes(srv_nbase[pk_srv[hv]] + ppos[hv] + 1, vul27_key[hv], ET["vulnerability"], sev27[hv])
-    put_edges(srv_ebase[pk_srv[hv]] + ppos[hv] + 1, pkg_key[hv], vul27_key[hv], R["vulnerable_to"])
-    tbase = 1 + n_pkg + n_vul
-    put_nodes(srv_nbase[tl_srv] + tbase[tl_srv] + tl_ti, tool_key, ET["tool"])
-    put_edges(srv_ebase[tl_srv] + tbase[tl_srv] + tl_ti, srv_key[tl_srv], tool_key, R["provides_tool"])
-    put_nodes(srv_nbase[cr_srv] + (tbase + n_tool)[cr_srv] + cr_k, cred_key, ET["credential"])
+    put_edges(ag_ebase[:-1], ix_prov, ix_agent, R["hosts"])
+    put_edges(srv_ebase, ix_agent[srv_agent], ix_srv, R["uses"])
+    dep_pos = srv_ebase[pk_srv] + ppos
+    put_edges(dep_pos, ix_srv[pk_srv], ix_pkg, R["depends_on"])
+    # add_edge drops a repeated (server, package, depends_on): same package id listed twice by one server
+    dkey = pk_srv * np.int64(N) + ix_pkg
+    _, dfirst = np.unique(dkey, return_index=True)
+    dup = np.ones(P, dtype=bool); dup[dfirst] = False
+    keep[dep_pos[dup]] = False
+    put_edges(dep_pos[hv] + 1, ix_pkg[hv], ix_v27, R["vulnerable_to"])
+    put_edges(srv_ebase[tl_srv] + tbase[tl_srv] + tl_ti, ix_srv[tl_srv], ix_tool, R["provides_tool"])
     cpos = srv_ebase[cr_srv] + (tbase + n_tool)[cr_srv] + cr_k * (1 + n_tool[cr_srv])
-    put_edges(cpos, srv_key[cr_srv], cred_key, R["exposes_cred"])
-    # REACHES_TOOL: every credential of a server × every tool of that server
-    rt_cred = np.repeat(np.arange(Cn, dtype=np.int64), n_tool[cr_srv])
-    rt_first = np.zeros(Cn + 1, dtype=np.int64); rt_first[1:] = np.cumsum(n_tool[cr_srv])
+    put_edges(cpos, ix_srv[cr_srv], ix_cred, R["exposes_cred"])
+    # REACHES_TOOL: every credential of a server x every tool of that server
+    nt_c = n_tool[cr_srv]
+    rt_cred = np.repeat(np.arange(Cn, dtype=np.int64), nt_c)
+    rt_first = np.zeros(Cn + 1, dtype=np.int64); rt_first[1:] = np.cumsum(nt_c)
     rt_ti = np.arange(int(rt_first[-1]), dtype=np.int64) - rt_first[rt_cred]
-    put_edges(cpos[rt_cred] + 1 + rt_ti, cred_key[rt_cred], tool_key[tl_first[cr_srv[rt_cred]] + rt_ti], R["reaches_tool"])
+    put_edges(cpos[rt_cred] + 1 + rt_ti, ix_cred[rt_cred], ix_tool[tl_first[cr_srv[rt_cred]] + rt_ti], R["reaches_tool"])
+    del rt_cred, rt_ti
 
-    seg_n = [nkey]; seg_t = [ntyp]; seg_v = [nsev]
-    seg_s = [e_s]; seg_d = [e_d]; seg_r = [e_r]
+    seg_s = [e_s[keep]]; seg_d = [e_d[keep]]; seg_r = [e_r[keep]]
+    del e_s, e_d, e_r, keep
 
     def tools_of(servers: np.ndarray):
-        """(repeat index, tool keys) for the tools of each listed server, in tool order."""
+        """(repeat index, tool node indices) for the tools of each listed server, in tool order."""
         cnt = n_tool[servers]
         rep = np.repeat(np.arange(servers.shape[0], dtype=np.int64), cnt)
         first = np.zeros(servers.shape[0] + 1, dtype=np.int64); first[1:] = np.cumsum(cnt)
         ti = np.arange(int(first[-1]), dtype=np.int64) - first[rep]
-        return rep, tool_key[tl_first[servers[rep]] + ti]
+        return rep, first, ix_tool[tl_first[servers[rep]] + ti]
 
     # ---- pending EXPLOITABLE_VIA edges of package-level vulnerabilities (builder.py:371-382, 971-1019)
     if kn.tool_capabilities and hv.size:
-        rep, tk = tools_of(pk_srv[hv])
-        seg_s.append(vul27_key[hv][rep]); seg_d.append(tk); seg_r.append(np.full(tk.shape[0], R["exploitable_via"], dtype=np.uint8))
+        rep, _, tk = tools_of(pk_srv[hv])
+        seg_s.append(ix_v27[rep]); seg_d.append(tk); seg_r.append(np.full(tk.shape[0], R["exploitable_via"], dtype=np.uint8))
 
-    # ---- blast-radius rows (scaffold :136-155 → builder.py:385-471)
-    cand = np.flatnonzero(_u01(seed, 13, pidx) < kn.vulnerable_package_rate)
-    if cand.size:
-        _, first_idx = np.unique(name_key[cand], return_index=True)
-        rows = cand[np.sort(first_idx)]                       # first instance of each name that drew "vulnerable", in generation order
-    else:
-        rows = cand
-    K = int(rows.shape[0])
-    v26_key = _mk(K_VULN26, np.arange(K, dtype=np.int64))
-    sev26 = ((pk_ai[rows] + pk_pi[rows]) % 4).astype(np.int8)
-    seg_n.append(v26_key); seg_t.append(np.full(K, ET["vulnerability"], dtype=np.uint8)); seg_v.append(sev26)
     if K:
         if kn.tool_capabilities and kn.blast_ecosystem:
-            rep, tk = tools_of(pk_srv[rows])
+            rep, first, tk = tools_of(pk_srv[rows])
             nt_rows = n_tool[pk_srv[rows]]
         else:
-            rep = np.zeros(0, dtype=np.int64); tk = np.zeros(0, dtype=np.int64); nt_rows = np.zeros(K, dtype=np.int64)
+            rep = np.zeros(0, dtype=np.int64); tk = np.zeros(0, dtype=np.int32); nt_rows = np.zeros(K, dtype=np.int64); first = None
         per_row = (1 if kn.blast_ecosystem else 0) + 1 + nt_rows
         rbase = np.cumsum(per_row) - per_row
         tot = int(per_row.sum())
-        bs = np.zeros(tot, dtype=np.int64); bd = np.zeros(tot, dtype=np.int64); br = np.zeros(tot, dtype=np.uint8)
+        bs = np.zeros(tot, dtype=np.int32); bd = np.zeros(tot, dtype=np.int32); br = np.zeros(tot, dtype=np.uint8)
         o = 0
         if kn.blast_ecosystem:                                  # pkg -> vuln resolves only with an ecosystem (builder.py:419-430)
-            bs[rbase] = pkg_key[rows]; bd[rbase] = v26_key; br[rbase] = R["vulnerable_to"]; o = 1
-        bs[rbase + o] = srv_key[pk_srv[rows]]; bd[rbase + o] = v26_key; br[rbase + o] = R["vulnerable_to"]
+            bs[rbase] = ix_pkg[rows]; bd[rbase] = ix_v26; br[rbase] = R["vulnerable_to"]; o = 1
+        bs[rbase + o] = ix_srv[pk_srv[rows]]; bd[rbase + o] = ix_v26; br[rbase + o] = R["vulnerable_to"]
         if rep.size:
-            first = np.zeros(K + 1, dtype=np.int64); first[1:] = np.cumsum(nt_rows)
             pos = rbase[rep] + o + 1 + (np.arange(rep.shape[0], dtype=np.int64) - first[rep])
-            bs[pos] = v26_key[rep]; bd[pos] = tk; br[pos] = R["exploitable_via"]
+            bs[pos] = ix_v26[rep]; bd[pos] = tk; br[pos] = R["exploitable_via"]
         seg_s.append(bs); seg_d.append(bd); seg_r.append(br)
 
     # ---- SHARES_CRED cliques (builder.py:493-507): all agents of a bucket share its first credential name;
@@ -380,8 +414,8 @@ def generate(agents: int, seed: int = 2145, knobs: Knobs = Knobs(), exact_rank: 
         b = kn.cred_bucket
         nb = (A + b - 1) // b
         sizes = np.minimum(b, A - np.arange(nb, dtype=np.int64) * b)
-        i_loc, j_loc = np.triu_indices(b, k=1)
-        sc_s, sc_d = [], []
+        i_loc, j_loc = np.triu_indices(b, k=1)                  # row-major: (a1, a2) ascending == the builder's nested loops
+        sc_s, sc_d, sc_b = [], [], []
         for size in np.unique(sizes):
             buckets = np.flatnonzero(sizes == size)
             sel = j_loc < size
@@ -389,32 +423,15 @@ def generate(agents: int, seed: int = 2145, knobs: Knobs = Knobs(), exact_rank: 
             sc_s.append((buckets[:, None] * b + ii[None, :]).ravel())
             sc_d.append((buckets[:, None] * b + jj[None, :]).ravel())
         sa, sd = np.concatenate(sc_s), np.concatenate(sc_d)
-        order = np.lexsort((sd, sa))                       # bucket-major, then (a1, a2) — cred_to_agents insertion order
-        sa, sd = sa[order], sd[order]
-        seg_s.append(agent_key[sa]); seg_d.append(agent_key[sd]); seg_r.append(np.full(sa.shape[0], R["shares_cred"], dtype=np.uint8))
+        if len(sc_s) > 1:                                       # the (single) short last bucket comes last in bucket order
+            order = np.argsort(sa // b, kind="stable")
+            sa, sd = sa[order], sd[order]
+        seg_s.append(ix_agent[sa]); seg_d.append(ix_agent[sd]); seg_r.append(np.full(sa.shape[0], R["shares_cred"], dtype=np.uint8))
 
-    # ---- first-wins de-duplication of nodes (add_node merge) and edges (add_edge key)
-    all_nk = np.concatenate(seg_n); all_nt = np.concatenate(seg_t); all_nv = np.concatenate(seg_v)
-    uniq, first_pos = np.unique(all_nk, return_index=True)
-    order = np.argsort(first_pos, kind="stable")
-    node_key = uniq[order]
-    node_pos = first_pos[order]
-    node_type = all_nt[node_pos]
-    node_sev = all_nv[node_pos]
-    N = int(node_key.shape[0])
-    lookup = np.empty(N, dtype=np.int64)
-    lookup[order] = np.arange(N, dtype=np.int64)           # index into `uniq` -> node index
-
-    def to_idx(keys: np.ndarray) -> np.ndarray:
-        return lookup[np.searchsorted(uniq, keys)]
-
-    es = to_idx(np.concatenate(seg_s)); ed = to_idx(np.concatenate(seg_d)); er = np.concatenate(seg_r)
-    ekey = (es * N + ed) * 32 + er
-    _, efirst = np.unique(ekey, return_index=True)
-    efirst.sort()
-    src, dst, rel = es[efirst].astype(np.int32), ed[efirst].astype(np.int32), er[efirst]
+    src = np.concatenate(seg_s); dst = np.concatenate(seg_d); rel = np.concatenate(seg_r)
+    del seg_s, seg_d, seg_r
     flags = np.full(src.shape[0], FLAG_T, dtype=np.uint8)
-    flags[efirst >= bidir_from] |= FLAG_B
+    flags[bidir_from:] |= FLAG_B
 
     # ---- id-string order surrogate: kind-major, then fields (exact among agents, whose ids are fixed-width)
     kind = node_key >> _KSHIFT

@@ -1,0 +1,373 @@
+#!/usr/bin/env python3
+"""bench.py — exposure-path traversals/sec on a synthetic estate (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload L|M2|M1|S] [--impl b200|reference]
+
+One *traversal* = for one finding node f: ``impact_of(f, max_depth=4)`` + f's
+derived exposure paths.  One *step* = one pass of that hot path
+over every finding of the estate (rank r takes the r-th contiguous slice of
+the finding list; the CSR is replicated by a one-time NCCL broadcast, no
+collective on the data path → total work is fixed, ``"scaling": "strong"``).
+
+Numbers on the JSON line
+  value        traversals/s with inputs (finding list, CSR) resident in HBM,
+               CUDA-event timed over K steps, max over ranks.
+  e2e          same metric through the public host API (``DeviceGraph.exposure_many``
+               → C ABI ``abb_exposure_host``): H2D of the finding ids and D2H of
+               every result array inside the timed region.
+  roofline     impact-walk kernels (frontier expansion): algorithmic bytes
+               (oracle-counted 8·N_exp + 6·M_scan + 8·N_disc) ÷ CUDA-event time
+               of the walk launches ÷ measured HBM peak.
+  cpu_baseline the CPU oracle port (oracle/oracle.c, OpenMP) on a bounded sample.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "exposure-path traversals/sec"
+UNIT = "traversals/s"
+WORKLOADS = {
+    # name: (agents, description)
+    "L": (215_000, "10M-node/100M-edge synthetic estate"),
+    "M2": (20_700, "1M-node/10M-edge synthetic estate"),
+    "M1": (2_000, "100K-node/1M-edge synthetic estate"),
+    "S": (300, "16K-node/150K-edge synthetic estate (smoke)"),
+}
+MAX_DEPTH = 4
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def hbm_peak() -> tuple[float, str]:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines: list[str] = []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *exc):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self) -> dict:
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_estate(workload: str, seed: int):
+    from agent_bom_b200 import estate
+    from agent_bom_b200.graph import csr as csrmod
+
+    agents, desc = WORKLOADS[workload]
+    t0 = time.perf_counter()
+    est = estate.generate(agents, seed, estate.BENCH_KNOBS, exact_rank=False)
+    t1 = time.perf_counter()
+    host = csrmod.from_arrays(None, est.node_type, est.src, est.dst, est.rel, est.flags, node_rank=est.node_rank)
+    t2 = time.perf_counter()
+    log(f"[bench] estate {workload}: {est.n_nodes:,} nodes / {est.n_edges:,} edges / {host.n_entries:,} adjacency entries per direction / "
+        f"{len(est.findings):,} findings (generate {t1 - t0:.1f}s, CSR build {t2 - t1:.1f}s)")
+    return est, host, desc
+
+
+def oracle_graph_from(host):
+    """The CPU baseline walks the same host CSR the device gets (its builder is parity-tested against the oracle's own in tests/test_abi.py)."""
+    from oracle import oracle as orc
+
+    return orc.OracleGraph(n_nodes=host.n_nodes, fwd_off=host.fwd_off, fwd_nbr=host.fwd_nbr, fwd_meta=host.fwd_meta, fwd_eid=host.fwd_eid,
+                           rev_off=host.rev_off, rev_nbr=host.rev_nbr, rev_meta=host.rev_meta, rev_eid=host.rev_eid, node_type=host.node_type)
+
+
+def cpu_traversals(og, findings: np.ndarray, node_rank: np.ndarray, threads: int = 0):
+    """One CPU pass of the hot path over `findings`; returns (seconds, impact WalkResult, n_path_rows)."""
+    from oracle import oracle as orc
+
+    t0 = time.perf_counter()
+    w = orc.impact_many(og, findings, MAX_DEPTH, threads=threads)
+    rows = orc.derived_paths(og, findings, node_rank, threads=threads)
+    return time.perf_counter() - t0, w, rows
+
+
+def sample_for_budget(og, findings, node_rank, budget_s: float):
+    """Largest evenly spaced sample of `findings` whose CPU pass fits ~budget_s (probe first)."""
+    probe = findings[:: max(1, len(findings) // 4000)][:4000]
+    dt, _, _ = cpu_traversals(og, probe, node_rank)
+    rate = len(probe) / max(dt, 1e-6)
+    n = int(min(len(findings), max(len(probe), rate * budget_s)))
+    stride = max(1, len(findings) // n)
+    return np.ascontiguousarray(findings[::stride][:n])
+
+
+def run_reference(args) -> int:
+    """--impl reference: the reference algorithm's CPU port on the host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import oracle as orc
+
+    est, host, desc = build_estate(args.workload, args.seed)
+    og = oracle_graph_from(host)
+    sample = sample_for_budget(og, est.findings, est.node_rank, args.cpu_budget)
+    times = []
+    for i in range(args.warmup + args.steps):
+        dt, w, rows = cpu_traversals(og, sample, est.node_rank)
+        if i >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = len(sample) * len(times) / total
+    cores = orc.num_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000.0 * total / len(times), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": f"{desc}, all finding nodes as sources", "estate": est.summary() | {"edges_by_relationship": None}, "max_depth": MAX_DEPTH},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{len(sample):,} of {len(est.findings):,} findings (every {max(1, len(est.findings) // len(sample))}th), oracle/oracle.c with OpenMP"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main() -> int:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="L", choices=sorted(WORKLOADS))
+    ap.add_argument("--seed", type=int, default=2145)
+    ap.add_argument("--batch", type=int, default=1 << 17, help="findings per launch batch")
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work per CPU-baseline pass")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--check", type=int, default=2000, help="findings spot-checked against the oracle before timing")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+
+    from agent_bom_b200 import _lib, dist as abdist
+    from agent_bom_b200.engine import DeviceGraph
+    from agent_bom_b200.torch_api import DevicePaths, DeviceWalk
+
+    info = abdist.init_from_env("nccl" if int(os.environ.get("WORLD_SIZE", "1")) > 1 else None)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback (use --impl reference for the CPU port)")
+    torch.cuda.set_device(info.local_rank)
+    device = torch.device("cuda", info.local_rank)
+    lib = _lib.load()
+
+    # ---- load path (untimed): rank 0 generates + builds the CSR, one NCCL broadcast replicates it
+    est = host = None
+    desc = WORKLOADS[args.workload][1]
+    if info.rank == 0:
+        est, host, desc = build_estate(args.workload, args.seed)
+    t0 = time.perf_counter()
+    tensors, n_nodes, n_entries = abdist.broadcast_csr(host, info, device)
+    findings_all = abdist.broadcast_array(est.findings if info.rank == 0 else None, info, device)
+    torch.cuda.synchronize()
+    t_bcast = time.perf_counter() - t0
+    dg = DeviceGraph.adopt(tensors, n_nodes, n_entries, info.local_rank)
+    lo, hi = abdist.shard_bounds(findings_all.shape[0], info.world, info.rank)
+    my = findings_all[lo:hi].contiguous()
+    my_host = my.cpu().numpy()
+    nq = int(my.shape[0])
+    batch = max(1, min(args.batch, nq))
+    batches = [(s, min(s + batch, nq)) for s in range(0, nq, batch)]
+    log(f"[bench] rank {info.rank}/{info.world}: {nq:,} findings in {len(batches)} batches of <= {batch:,}; CSR replicate {t_bcast:.2f}s ({dg.nbytes / 1e9:.2f} GB)")
+
+    # ---- device-resident leg: buffers sized by a first fitted pass
+    spec = DeviceGraph.spec_impact_of(MAX_DEPTH)
+    walk = DeviceWalk(dg, spec, batch, node_cap=1 << 20)
+    paths = DevicePaths(dg, batch)
+    need_nodes = need_rows = 0
+    tot_nodes = tot_rows = 0
+    for s, e in batches:
+        n_need, _ = walk.launch_fitted(my[s:e])
+        rows = paths.run_fitted(my[s:e])
+        need_nodes, need_rows = max(need_nodes, n_need), max(need_rows, rows)
+        tot_nodes += n_need; tot_rows += rows
+    walk.reserve(need_nodes); paths.reserve(need_rows)
+    torch.cuda.synchronize()
+
+    # ---- parity spot check against the oracle (rank 0): an invalid run must not print a number
+    og = None
+    if info.rank == 0 and (args.check > 0 or not args.no_cpu_baseline):
+        from oracle import oracle as orc
+
+        og = oracle_graph_from(host)
+    if info.rank == 0 and args.check > 0:
+        k = min(args.check, nq)
+        sel = my_host[:: max(1, nq // k)][:k]
+        got_w, got_p = dg.exposure_many(sel, MAX_DEPTH)
+        want_w = orc.impact_many(og, sel, MAX_DEPTH)
+        want_p = orc.derived_paths(og, sel, est.node_rank)
+        ok = np.array_equal(got_w.count, np.diff(want_w.off).astype(np.int32)) and np.array_equal(got_w.hist, want_w.hist) and np.array_equal(got_w.maxd, want_w.maxd)
+        for q in range(len(sel)):
+            if not ok:
+                break
+            a, b = int(want_w.off[q]), int(want_w.off[q + 1])
+            ok = np.array_equal(got_w.slice(q), want_w.nodes[a:b])
+        ok = ok and np.array_equal(got_p.hops, want_p.hops) and np.array_equal(got_p.rels, want_p.rels) and np.array_equal(got_p.ncred, want_p.ncred)
+        if not ok:
+            raise SystemExit("[bench] PARITY FAILURE against the CPU oracle — refusing to report a number")
+        log(f"[bench] parity spot check: {len(sel):,} findings bit-identical to the oracle")
+
+    def one_step(walk_events=None):
+        for s, e in batches:
+            if walk_events is not None:
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
+            walk.launch(my[s:e])
+            if walk_events is not None:
+                ev1.record()
+                walk_events.append((ev0, ev1))
+            paths.count(my[s:e])
+            paths.fill(my[s:e])
+
+    for _ in range(args.warmup):
+        one_step()
+    torch.cuda.synchronize()
+    abdist.barrier(info)
+    launches0 = lib.abb_launch_count()
+    walk_events: list = []
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(info.local_rank) as clocks:
+        torch.cuda.synchronize()
+        start.record()
+        for _ in range(args.steps):
+            one_step(walk_events)
+        end.record()
+        torch.cuda.synchronize()
+    abdist.barrier(info)
+    launches = lib.abb_launch_count() - launches0
+    dev_ms = start.elapsed_time(end)
+    walk_ms = sum(a.elapsed_time(b) for a, b in walk_events)
+    dev_ms_max = abdist.max_over_ranks(dev_ms, info, device)
+    total_findings = int(findings_all.shape[0])
+    value = total_findings * args.steps / (dev_ms_max / 1000.0)
+
+    # ---- end-to-end leg: host finding ids in, every result array out, through the C-ABI host call
+    def e2e_step():
+        h2d = d2h = 0
+        for s, e in batches:
+            w, p = dg.exposure_many(my_host[s:e], MAX_DEPTH, collect=False)
+            h2d += w[1] + p[1]; d2h += w[2] + p[2]
+        return h2d, d2h
+
+    for _ in range(args.warmup):
+        e2e_step()
+    torch.cuda.synchronize()
+    abdist.barrier(info)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        h2d, d2h = e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    abdist.barrier(info)
+    e2e_s_max = abdist.max_over_ranks(e2e_s, info, device)
+    e2e_value = total_findings * args.steps / e2e_s_max
+    h2d_all = abdist.sum_over_ranks(h2d, info, device)
+    d2h_all = abdist.sum_over_ranks(d2h, info, device)
+
+    # ---- roofline of the frontier-expansion (impact walk) launches + CPU baseline, rank 0
+    roofline = cpu_baseline = None
+    peak, peak_src = hbm_peak()
+    if info.rank == 0:
+        if og is not None and not args.no_cpu_baseline:
+            sample = sample_for_budget(og, my_host, est.node_rank, args.cpu_budget)
+            dt, w, _rows = cpu_traversals(og, sample, est.node_rank)
+            bytes_per = w.algorithmic_bytes / len(sample)
+            cpu_baseline = {"value": len(sample) / dt, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
+                            "sample": f"{len(sample):,} of {nq:,} findings (evenly spaced), oracle/oracle.c + OpenMP, {dt:.1f}s"}
+            algo_bytes_per_step = bytes_per * nq
+            walk_ms_per_step = walk_ms / args.steps
+            achieved = algo_bytes_per_step / (walk_ms_per_step / 1000.0) / 1e9
+            roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                        "kernel": "walk_smem_kernel (+ overflow tiers) of abb_walk_launch", "algorithmic_bytes_per_traversal": bytes_per,
+                        "bytes_estimated_from": f"oracle counters on {len(sample):,} sampled findings", "walk_ms_per_step": walk_ms_per_step, "peak_source": peak_src}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": info.world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {
+                "workload": f"{desc}, all finding nodes as sources, sharded across {info.world} GPU(s)", "nodes": n_nodes, "adjacency_entries_per_direction": n_entries,
+                "findings": total_findings, "max_depth": MAX_DEPTH, "batch": batch, "seed": args.seed,
+                "estate_knobs": "creds_per_server=20, cred_bucket=80, vulns_per_server=8 (agent_bom_b200.estate.BENCH_KNOBS)",
+                "l2": "inputs larger than L2 (CSR >> 126 MB; no flush)" if dg.nbytes > 400e6 else "CSR smaller than L2; no flush (reported as is)",
+                "reached_nodes_per_step_rank0": tot_nodes, "path_rows_per_step_rank0": tot_rows, "csr_replicate_s": t_bcast,
+            },
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(d2h_all), "ms_per_step": 1000.0 * e2e_s_max / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks.summary(),
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    abdist.barrier(info)
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())

@@ -535,73 +535,121 @@ static int cmp_rank(const void *x, const void *y, void *rk) {
     return (a > b) - (a < b);
 }
 
-/* node_rank[u] = position of u's id in the sorted list of all id strings
-   (the reference sorts agent ids as strings, graph.py:751). */
-orc_paths *orc_derived_paths(const orc_graph *g, const int32_t *findings, int64_t n_findings, const int32_t *node_rank) {
-    vec32 hops = {0}, nc = {0}, nt = {0}; vec32 rels = {0};
-    vec32 servers = {0}, agents = {0};
+/* rows of one finding, appended to the given vectors; returns the row count */
+static int64_t paths_one(const orc_graph *g, int32_t f, const int32_t *node_rank, vec32 *hops, vec32 *rels, vec32 *nc, vec32 *nt,
+                         vec32 *servers, vec32 *agents) {
     int64_t np = 0;
-    for (int64_t fi = 0; fi < n_findings; fi++) {
-        int32_t f = findings[fi];
-        if (f < 0 || f >= g->n_nodes) continue;
-        uint8_t ft = g->node_type[f];
-        if (ft != ET_VULN && ft != ET_MISCONF) continue;                         /* :708-710 */
-        for (uint32_t p = g->rev_off[f]; p < g->rev_off[f + 1]; p++) {           /* :711 incoming[finding] = originals only */
-            uint8_t m = g->rev_meta[p];
-            if (m & META_REVCOPY) continue;
-            if ((m & META_REL) != REL_VULNERABLE_TO) continue;                   /* :712-713 */
-            int32_t vs = g->rev_nbr[p];
-            if (g->node_type[vs] == GHOST) continue;                             /* :714-716 */
-            servers.n = 0;
-            if (g->node_type[vs] == ET_SERVER) v32_push(&servers, vs);           /* :719-720 */
-            else {
-                for (uint32_t p2 = g->rev_off[vs]; p2 < g->rev_off[vs + 1]; p2++) {   /* :722-726 */
-                    uint8_t m2 = g->rev_meta[p2];
-                    if (m2 & META_REVCOPY) continue;
-                    if ((m2 & META_REL) != REL_DEPENDS_ON) continue;
-                    int32_t sp = g->rev_nbr[p2];
-                    if (g->node_type[sp] == ET_SERVER) v32_push(&servers, sp);
-                }
+    if (f < 0 || f >= g->n_nodes) return 0;
+    uint8_t ft = g->node_type[f];
+    if (ft != ET_VULN && ft != ET_MISCONF) return 0;                             /* :708-710 */
+    for (uint32_t p = g->rev_off[f]; p < g->rev_off[f + 1]; p++) {               /* :711 incoming[finding] = originals only */
+        uint8_t m = g->rev_meta[p];
+        if (m & META_REVCOPY) continue;
+        if ((m & META_REL) != REL_VULNERABLE_TO) continue;                       /* :712-713 */
+        int32_t vs = g->rev_nbr[p];
+        if (g->node_type[vs] == GHOST) continue;                                 /* :714-716 */
+        servers->n = 0;
+        if (g->node_type[vs] == ET_SERVER) v32_push(servers, vs);                /* :719-720 */
+        else {
+            for (uint32_t p2 = g->rev_off[vs]; p2 < g->rev_off[vs + 1]; p2++) {  /* :722-726 */
+                uint8_t m2 = g->rev_meta[p2];
+                if (m2 & META_REVCOPY) continue;
+                if ((m2 & META_REL) != REL_DEPENDS_ON) continue;
+                int32_t sp = g->rev_nbr[p2];
+                if (g->node_type[sp] == ET_SERVER) v32_push(servers, sp);
             }
-            for (int64_t si = 0; si < servers.n; si++) {
-                int32_t srv = servers.p[si];
-                agents.n = 0;
-                for (uint32_t p3 = g->rev_off[srv]; p3 < g->rev_off[srv + 1]; p3++) {  /* :729-736 */
-                    uint8_t m3 = g->rev_meta[p3];
-                    if (m3 & META_REVCOPY) continue;
-                    if ((m3 & META_REL) != REL_USES) continue;
-                    int32_t a = g->rev_nbr[p3];
-                    uint8_t at = g->node_type[a];
-                    if (at == ET_AGENT || at == ET_USER || at == ET_SERVICE_ACCOUNT) v32_push(&agents, a);
-                }
-                if (agents.n == 0) v32_push(&agents, srv);                       /* :737-738 */
-                int32_t ncred = 0, ntool = 0;
-                for (uint32_t p4 = g->fwd_off[srv]; p4 < g->fwd_off[srv + 1]; p4++) {  /* :740-749 outgoing = originals only */
-                    uint8_t m4 = g->fwd_meta[p4];
-                    if (m4 & META_REVCOPY) continue;
-                    if (g->node_type[g->fwd_nbr[p4]] == GHOST) continue;
-                    if ((m4 & META_REL) == REL_EXPOSES_CRED) ncred++;
-                    else if ((m4 & META_REL) == REL_PROVIDES_TOOL) ntool++;
-                }
-                qsort_r(agents.p, (size_t)agents.n, 4, cmp_rank, (void *)node_rank);   /* :751 sorted(set(agent_ids)) */
-                for (int64_t ai = 0; ai < agents.n; ai++) {
-                    if (ai && agents.p[ai] == agents.p[ai - 1]) continue;
-                    int32_t a = agents.p[ai];
-                    int32_t hp[4]; int nh = 0;
-                    hp[nh++] = a; hp[nh++] = srv; if (vs != srv) hp[nh++] = vs; hp[nh++] = f;   /* :752-755 */
-                    v32_push(&hops, a); v32_push(&hops, srv); v32_push(&hops, vs != srv ? vs : -1); v32_push(&hops, f);
-                    for (int k = 0; k < 3; k++) v32_push(&rels, k + 1 < nh ? first_rel(g, hp[k], hp[k + 1]) : -2);
-                    v32_push(&nc, ncred); v32_push(&nt, ntool);
-                    np++;
-                }
+        }
+        for (int64_t si = 0; si < servers->n; si++) {
+            int32_t srv = servers->p[si];
+            agents->n = 0;
+            for (uint32_t p3 = g->rev_off[srv]; p3 < g->rev_off[srv + 1]; p3++) {     /* :729-736 */
+                uint8_t m3 = g->rev_meta[p3];
+                if (m3 & META_REVCOPY) continue;
+                if ((m3 & META_REL) != REL_USES) continue;
+                int32_t a = g->rev_nbr[p3];
+                uint8_t at = g->node_type[a];
+                if (at == ET_AGENT || at == ET_USER || at == ET_SERVICE_ACCOUNT) v32_push(agents, a);
+            }
+            if (agents->n == 0) v32_push(agents, srv);                           /* :737-738 */
+            int32_t ncred = 0, ntool = 0;
+            for (uint32_t p4 = g->fwd_off[srv]; p4 < g->fwd_off[srv + 1]; p4++) {     /* :740-749 outgoing = originals only */
+                uint8_t m4 = g->fwd_meta[p4];
+                if (m4 & META_REVCOPY) continue;
+                if (g->node_type[g->fwd_nbr[p4]] == GHOST) continue;
+                if ((m4 & META_REL) == REL_EXPOSES_CRED) ncred++;
+                else if ((m4 & META_REL) == REL_PROVIDES_TOOL) ntool++;
+            }
+            qsort_r(agents->p, (size_t)agents->n, 4, cmp_rank, (void *)node_rank);     /* :751 sorted(set(agent_ids)) */
+            for (int64_t ai = 0; ai < agents->n; ai++) {
+                if (ai && agents->p[ai] == agents->p[ai - 1]) continue;
+                int32_t a = agents->p[ai];
+                int32_t hp[4]; int nh = 0;
+                hp[nh++] = a; hp[nh++] = srv; if (vs != srv) hp[nh++] = vs; hp[nh++] = f;     /* :752-755 */
+                v32_push(hops, a); v32_push(hops, srv); v32_push(hops, vs != srv ? vs : -1); v32_push(hops, f);
+                for (int k = 0; k < 3; k++) v32_push(rels, k + 1 < nh ? first_rel(g, hp[k], hp[k + 1]) : -2);
+                v32_push(nc, ncred); v32_push(nt, ntool);
+                np++;
             }
         }
     }
+    return np;
+}
+
+/* node_rank[u] = position of u's id in the sorted list of all id strings
+   (the reference sorts agent ids as strings, graph.py:751).  Findings are
+   independent, so they are spread over the host threads and the per-thread
+   row blocks are stitched back in finding order (the reference's emission order). */
+orc_paths *orc_derived_paths(const orc_graph *g, const int32_t *findings, int64_t n_findings, const int32_t *node_rank, int threads) {
+    int nt_ = 1;
+#ifdef _OPENMP
+    nt_ = threads > 0 ? threads : omp_get_max_threads();
+#endif
+    (void)threads;
+    typedef struct { vec32 hops, rels, nc, nt, servers, agents; } tbuf;
+    tbuf *T = (tbuf *)calloc((size_t)nt_, sizeof(tbuf));
+    int32_t *f_thr = (int32_t *)malloc((size_t)(n_findings + 1) * 4);
+    int64_t *f_start = (int64_t *)malloc((size_t)(n_findings + 1) * 8);
+    int64_t *f_cnt = (int64_t *)calloc((size_t)n_findings + 1, 8);
+#ifdef _OPENMP
+#pragma omp parallel num_threads(nt_)
+#endif
+    {
+        int t = 0;
+#ifdef _OPENMP
+        t = omp_get_thread_num();
+#endif
+        tbuf *b = &T[t];
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 256)
+#endif
+        for (int64_t fi = 0; fi < n_findings; fi++) {
+            f_thr[fi] = t; f_start[fi] = b->nc.n;
+            f_cnt[fi] = paths_one(g, findings[fi], node_rank, &b->hops, &b->rels, &b->nc, &b->nt, &b->servers, &b->agents);
+        }
+    }
+    int64_t *off = (int64_t *)malloc((size_t)(n_findings + 1) * 8);
+    off[0] = 0;
+    for (int64_t fi = 0; fi < n_findings; fi++) off[fi + 1] = off[fi] + f_cnt[fi];
+    int64_t np = off[n_findings];
     orc_paths *out = (orc_paths *)calloc(1, sizeof(orc_paths));
     out->n_paths = np;
-    out->hops = hops.p; out->ncred = nc.p; out->ntool = nt.p;
-    out->rels = (int8_t *)malloc((size_t)np * 3 + 1);
-    for (int64_t i = 0; i < np * 3; i++) out->rels[i] = (int8_t)rels.p[i];
-    free(rels.p); free(servers.p); free(agents.p);
+    out->hops = (int32_t *)malloc((size_t)np * 16 + 16);
+    out->rels = (int8_t *)malloc((size_t)np * 3 + 16);
+    out->ncred = (int32_t *)malloc((size_t)np * 4 + 16);
+    out->ntool = (int32_t *)malloc((size_t)np * 4 + 16);
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(nt_)
+#endif
+    for (int64_t fi = 0; fi < n_findings; fi++) {
+        if (!f_cnt[fi]) continue;
+        tbuf *b = &T[f_thr[fi]];
+        int64_t s = f_start[fi], c = f_cnt[fi], o = off[fi];
+        memcpy(out->hops + o * 4, b->hops.p + s * 4, (size_t)c * 16);
+        memcpy(out->ncred + o, b->nc.p + s, (size_t)c * 4);
+        memcpy(out->ntool + o, b->nt.p + s, (size_t)c * 4);
+        for (int64_t i = 0; i < c * 3; i++) out->rels[o * 3 + i] = (int8_t)b->rels.p[s * 3 + i];
+    }
+    for (int t = 0; t < nt_; t++) { free(T[t].hops.p); free(T[t].rels.p); free(T[t].nc.p); free(T[t].nt.p); free(T[t].servers.p); free(T[t].agents.p); }
+    free(T); free(f_thr); free(f_start); free(f_cnt); free(off);
     return out;
 }

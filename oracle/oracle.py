@@ -62,7 +62,7 @@ def lib():
         L.orc_shortest_path.restype = i64
         L.orc_shortest_path.argtypes = [vp, i32, i32, vp, i64]
         L.orc_derived_paths.restype = vp
-        L.orc_derived_paths.argtypes = [vp, vp, i64, vp]
+        L.orc_derived_paths.argtypes = [vp, vp, i64, vp, C.c_int]
         for name in ("total", "total_edges"):
             f = getattr(L, f"orc_result_{name}")
             f.restype, f.argtypes = i64, [vp]
@@ -273,11 +273,11 @@ class PathRows:
     ntool: np.ndarray
 
 
-def derived_paths(g: OracleGraph, findings, node_rank) -> PathRows:
+def derived_paths(g: OracleGraph, findings, node_rank, threads: int = 0) -> PathRows:
     f = _i32(findings)
     rk = _i32(node_rank)
     L = lib()
-    p = L.orc_derived_paths(g.cptr(), f.ctypes.data, len(f), rk.ctypes.data)
+    p = L.orc_derived_paths(g.cptr(), f.ctypes.data, len(f), rk.ctypes.data, threads)
     n = L.orc_paths_count(p)
     out = PathRows(
         hops=_np_from(L.orc_paths_hops(p), n * 4, np.int32).reshape(n, 4),
