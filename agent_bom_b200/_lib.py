@@ -74,6 +74,7 @@ EXPORTS = {
     "abb_graph_adopt": (C.c_int, [C.c_int, C.POINTER(Csr), C.POINTER(vp)]),
     "abb_graph_view": (C.c_int, [vp, C.POINTER(Csr)]),
     "abb_graph_bytes": (i64, [vp]),
+    "abb_graph_set_dedup": (C.c_int, [vp, C.c_int]),
     "abb_graph_device": (C.c_int, [vp]),
     "abb_graph_free": (None, [vp]),
     "abb_spec_impact_of": (WalkSpec, [i32]),

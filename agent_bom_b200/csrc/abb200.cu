@@ -17,6 +17,7 @@
 #include <cub/cub.cuh>
 
 #include "../../include/abb200.h"
+#include "dedup.cuh"
 #include "paths.cuh"
 #include "reach.cuh"
 #include "walk.cuh"
@@ -80,8 +81,7 @@ extern "C" int abb_csr_build_host(int32_t n_nodes, int64_t n_edges, const int32_
     for (int64_t i = 0; i < n_edges; i++) {
         int32_t s = src[i], d = dst[i];
         uint8_t fl = flags[i];
-        uint8_t m = static_cast<uint8_t>((rel[i] & ABB_META_REL_MASK) | ((fl & ABB_EDGE_TRAVERSABLE) ? ABB_META_TRAVERSABLE : 0) |
-                                         ((fl & ABB_EDGE_BIDIRECTIONAL) ? ABB_META_BIDIRECTIONAL : 0));
+        uint8_t m = static_cast<uint8_t>((rel[i] & ABB_META_REL_MASK) | ((fl & ABB_EDGE_TRAVERSABLE) ? ABB_META_TRAVERSABLE : 0));
         uint32_t e2 = static_cast<uint32_t>(i) * 2u;
         uint64_t p = fc[s]++; fwd_nbr[p] = d; fwd_meta[p] = m; fwd_eid[p] = e2;
         uint64_t r = rc[d]++; rev_nbr[r] = s; rev_meta[r] = m; rev_eid[r] = e2;
@@ -90,6 +90,15 @@ extern "C" int abb_csr_build_host(int32_t n_nodes, int64_t n_edges, const int32_
             p = fc[d]++; fwd_nbr[p] = s; fwd_meta[p] = mr; fwd_eid[p] = e2 + 1;
             r = rc[s]++; rev_nbr[r] = d; rev_meta[r] = mr; rev_eid[r] = e2 + 1;
         }
+    }
+    // FIRST_PAIR: first entry of a row with a given neighbour (row-stamped scratch, O(E))
+    std::vector<int32_t> stamp(static_cast<size_t>(n_nodes) + 1, -1);
+    for (int pass = 0; pass < 2; pass++) {
+        const uint32_t *off = pass ? rev_off : fwd_off; const int32_t *nb = pass ? rev_nbr : fwd_nbr; uint8_t *me = pass ? rev_meta : fwd_meta;
+        std::fill(stamp.begin(), stamp.end(), -1);
+        for (int32_t u = 0; u < n_nodes; u++)
+            for (uint32_t p = off[u]; p < off[u + 1]; p++)
+                if (stamp[nb[p]] != u) { stamp[nb[p]] = u; me[p] |= ABB_META_FIRST_PAIR; }
     }
     return ABB_OK;
 }
@@ -164,13 +173,23 @@ struct abb_graph {
     bool walk_timed = false, paths_timed = false;
     // tier bookkeeping
     DevBuf ctl, ov1, ov2;
+    // tier G1: many per-warp slots (bitmap over all nodes + a bounded queue); tier GX: a few slots that can hold a whole-graph walk
     DevBuf g_bitmap, g_queue, g_par, g_dep;
     int g_slots = 0; int64_t g_words = 0, g_qcap = 0;
+    DevBuf x_bitmap, x_queue, x_par, x_dep;
+    int x_slots = 0; int64_t x_qcap = 0;
+    // root-frontier de-duplication workspace
+    DevBuf dd_sig, dd_ssig, dd_q, dd_sq, dd_head, dd_gid, dd_hp, dd_glen, dd_goff, dd_arena, dd_memoff, dd_memsrc, dd_memstate, dd_indiv, dd_cnt, dd_tmp;
+    DevBuf dd_gstart, dd_gcount, dd_gmaxd, dd_gflags, dd_ghist;
+    bool dedup_enabled = true;
     DevBuf identity_rank;
     // host-API staging
     DevBuf d_roots, d_root_off, d_targets, d_qstart, d_qcount, d_qmaxd, d_qflags, d_qestart, d_qecount, d_qhist;
     DevBuf d_nodes, d_parent, d_depth, d_edges, d_totals;
     int64_t hint_nodes = 0, hint_edges = 0;
+    // graph-constant server fan-out table (built on first use)
+    DevBuf srv_cred, srv_tool;
+    bool srv_table_ready = false;
     // paths staging
     DevBuf p_findings, p_counts, p_off, p_hops, p_rels, p_ncred, p_ntool, p_scan_tmp;
     int64_t hint_rows = 0;
@@ -190,21 +209,32 @@ static int graph_finish_init(abb_graph *g) {
     g->sm_count = prop.multiProcessorCount;
     CUDA_TRY(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
     for (auto &e : g->ev) CUDA_TRY(cudaEventCreate(&e));
-    if (int rc = g->ctl.ensure(16 * sizeof(unsigned long long))) return rc;
-    // tier G scratch: a handful of per-warp slots, each able to hold a whole-graph traversal
+    if (int rc = g->ctl.ensure(64 * sizeof(unsigned long long))) return rc;
     const int64_t n = g->v.n;
     g->g_words = (n + 31) / 32 + 1;
-    g->g_qcap = n + 4096;
-    const int64_t per_slot = g->g_words * 4 + g->g_qcap * 12;
-    int64_t slots = (2ll << 30) / std::max<int64_t>(per_slot, 1);
-    slots = std::max<int64_t>(4, std::min<int64_t>(64, slots));
-    slots = (slots / 4) * 4;
-    g->g_slots = static_cast<int>(slots);
-    if (int rc = g->g_bitmap.ensure(static_cast<size_t>(slots * g->g_words * 4))) return rc;
-    if (int rc = g->g_queue.ensure(static_cast<size_t>(slots * g->g_qcap * 4))) return rc;
-    if (int rc = g->g_par.ensure(static_cast<size_t>(slots * g->g_qcap * 4))) return rc;
-    if (int rc = g->g_dep.ensure(static_cast<size_t>(slots * g->g_qcap * 4))) return rc;
-    CUDA_TRY(cudaMemset(g->g_bitmap.p, 0, static_cast<size_t>(slots * g->g_words * 4)));
+    // tier G1: 8 warps per SM, queue bounded at 64K entries (or the whole graph if smaller)
+    g->g_qcap = std::min<int64_t>(n + 4096, 1 << 16);
+    g->g_slots = g->sm_count * 8;
+    {
+        const size_t sl = static_cast<size_t>(g->g_slots);
+        if (int rc = g->g_bitmap.ensure(sl * g->g_words * 4)) return rc;
+        if (int rc = g->g_queue.ensure(sl * g->g_qcap * 4)) return rc;
+        if (int rc = g->g_par.ensure(sl * g->g_qcap * 4)) return rc;
+        if (int rc = g->g_dep.ensure(sl * g->g_qcap * 4)) return rc;
+        CUDA_TRY(cudaMemset(g->g_bitmap.p, 0, sl * g->g_words * 4));
+    }
+    // tier GX: 8 slots that can hold any walk (every node once + re-seeded roots)
+    g->x_qcap = n + 4096;
+    g->x_slots = 8;
+    {
+        const size_t sl = static_cast<size_t>(g->x_slots);
+        if (int rc = g->x_bitmap.ensure(sl * g->g_words * 4)) return rc;
+        if (int rc = g->x_queue.ensure(sl * g->x_qcap * 4)) return rc;
+        if (int rc = g->x_par.ensure(sl * g->x_qcap * 4)) return rc;
+        if (int rc = g->x_dep.ensure(sl * g->x_qcap * 4)) return rc;
+        CUDA_TRY(cudaMemset(g->x_bitmap.p, 0, sl * g->g_words * 4));
+    }
+    if (const char *e = getenv("ABB_DEDUP")) g->dedup_enabled = atoi(e) != 0;
     if (!g->v.rank) {
         if (int rc = g->identity_rank.ensure(static_cast<size_t>(n + 1) * 4)) return rc;
         std::vector<int32_t> id(static_cast<size_t>(n));
@@ -288,6 +318,12 @@ extern "C" int abb_graph_view(const abb_graph *g, abb_csr *out) {
     return ABB_OK;
 }
 extern "C" int64_t abb_graph_bytes(const abb_graph *g) { return g ? g->bytes : 0; }
+extern "C" int abb_graph_set_dedup(abb_graph *g, int enabled) {
+    if (!g) return fail(ABB_ERR_ARG, "null graph");
+    std::lock_guard<std::mutex> lk(g->mu);
+    g->dedup_enabled = enabled != 0;
+    return ABB_OK;
+}
 extern "C" int abb_graph_device(const abb_graph *g) { return g ? g->device : -1; }
 
 extern "C" void abb_graph_free(abb_graph *g) {
@@ -295,10 +331,10 @@ extern "C" void abb_graph_free(abb_graph *g) {
     DeviceGuard dg(g->device);
     if (g->stream) { cudaStreamSynchronize(g->stream); cudaStreamDestroy(g->stream); }
     for (auto &e : g->ev) if (e) cudaEventDestroy(e);
-    for (DevBuf *b : {&g->ctl, &g->ov1, &g->ov2, &g->g_bitmap, &g->g_queue, &g->g_par, &g->g_dep, &g->identity_rank, &g->d_roots, &g->d_root_off,
+    for (DevBuf *b : {&g->ctl, &g->ov1, &g->ov2, &g->g_bitmap, &g->g_queue, &g->g_par, &g->g_dep, &g->x_bitmap, &g->x_queue, &g->x_par, &g->x_dep, &g->dd_sig, &g->dd_ssig, &g->dd_q, &g->dd_sq, &g->dd_head, &g->dd_gid, &g->dd_hp, &g->dd_glen, &g->dd_goff, &g->dd_arena, &g->dd_memoff, &g->dd_memsrc, &g->dd_memstate, &g->dd_indiv, &g->dd_cnt, &g->dd_tmp, &g->dd_gstart, &g->dd_gcount, &g->dd_gmaxd, &g->dd_gflags, &g->dd_ghist, &g->identity_rank, &g->d_roots, &g->d_root_off,
                       &g->d_targets, &g->d_qstart, &g->d_qcount, &g->d_qmaxd, &g->d_qflags, &g->d_qestart, &g->d_qecount, &g->d_qhist, &g->d_nodes,
                       &g->d_parent, &g->d_depth, &g->d_edges, &g->d_totals, &g->p_findings, &g->p_counts, &g->p_off, &g->p_hops, &g->p_rels,
-                      &g->p_ncred, &g->p_ntool, &g->p_scan_tmp})
+                      &g->p_ncred, &g->p_ntool, &g->p_scan_tmp, &g->srv_cred, &g->srv_tool})
         b->release();
     if (g->owned) for (void *p : g->owned_ptrs) cudaFree(p);
     delete g;
@@ -358,7 +394,6 @@ extern "C" abb_walk_spec abb_spec_distances_along(uint32_t rel_mask, uint32_t em
 
 // ------------------------------------------------------------------ walk dispatch
 constexpr int S1_H = 1024, S1_Q = 512, S1_WARPS = 8;
-constexpr int S2_H = 16384, S2_Q = 8192, S2_WARPS = 1;
 
 template <int H, int Q, int WARPS, bool PAR, bool META, bool BUD>
 static int launch_smem(const abb_graph *g, const WalkArgs &A, int64_t max_items, cudaStream_t st) {
@@ -390,8 +425,8 @@ static int launch_smem_variant(const abb_graph *g, const WalkArgs &A, int64_t ma
     return fail(ABB_ERR_ARG, "unreachable");
 }
 
-static int launch_global_variant(const abb_graph *g, const WalkArgs &A, bool meta, bool bud, cudaStream_t st) {
-    const int blocks = g->g_slots / 4;
+static int launch_global_variant(const WalkArgs &A, int slots, bool meta, bool bud, cudaStream_t st) {
+    const int blocks = std::max(1, slots / 4);
     if (meta && bud) walk_global_kernel<true, true><<<blocks, 128, 0, st>>>(A);
     else if (meta) walk_global_kernel<true, false><<<blocks, 128, 0, st>>>(A);
     else if (bud) walk_global_kernel<false, true><<<blocks, 128, 0, st>>>(A);
@@ -401,8 +436,30 @@ static int launch_global_variant(const abb_graph *g, const WalkArgs &A, bool met
     return ABB_OK;
 }
 
-// enqueue the three tiers; each later tier reads its work list + count from device memory
-static int enqueue_walk(abb_graph *g, const abb_walk_spec *spec, const abb_walk_io *io, cudaStream_t st) {
+// Three tiers on one stream.  `A` carries spec/io and the first tier's work list (qlist/nq/nq_dev); every later
+// tier reads its work list and count from device memory, so nothing here waits for the GPU.
+//   S1  warp + shared-memory hash/queue            (<= 512 queue entries)
+//   G1  warp + global bitmap, bounded queue slot   (<= 64K queue entries), 8 warps per SM
+//   GX  warp + global bitmap, whole-graph slot     (anything)
+// ctl: 12 counters — tier t uses ctl[4t .. 4t+3] = {work cursor, overflow count, fatal flag, -}
+static int enqueue_tiers(abb_graph *g, WalkArgs A, int64_t max_items, unsigned long long *ctl, int32_t *ov1, int32_t *ov2, cudaStream_t st) {
+    const uint32_t fl = A.spec.flags;
+    const bool par = fl & ABB_WALK_PARENTS;
+    const bool meta = A.spec.rel_mask != 0xFFFFFFFFu || (fl & ABB_WALK_TRAVERSABLE_ONLY);
+    const bool bud = A.spec.max_nodes >= 0 || A.spec.max_edges >= 0;
+    A.ctl = ctl; A.overflow = ov1;
+    if (int rc = launch_smem_variant<S1_H, S1_Q, S1_WARPS>(g, A, max_items, par, meta, bud, st)) return rc;
+    A.qlist = ov1; A.nq = 0; A.nq_dev = ctl + 1; A.ctl = ctl + 4; A.overflow = ov2;
+    A.g_bitmap = g->g_bitmap.as<uint32_t>(); A.g_queue = g->g_queue.as<int32_t>(); A.g_par = g->g_par.as<int32_t>(); A.g_dep = g->g_dep.as<int32_t>();
+    A.g_words = g->g_words; A.g_qcap = g->g_qcap;
+    if (int rc = launch_global_variant(A, g->g_slots, meta, bud, st)) return rc;
+    A.qlist = ov2; A.nq_dev = ctl + 5; A.ctl = ctl + 8; A.overflow = nullptr;
+    A.g_bitmap = g->x_bitmap.as<uint32_t>(); A.g_queue = g->x_queue.as<int32_t>(); A.g_par = g->x_par.as<int32_t>(); A.g_dep = g->x_dep.as<int32_t>();
+    A.g_qcap = g->x_qcap;
+    return launch_global_variant(A, g->x_slots, meta, bud, st);
+}
+
+static int check_walk_io(const abb_walk_spec *spec, const abb_walk_io *io) {
     if (!spec || !io) return fail(ABB_ERR_ARG, "null spec/io");
     if (io->n_queries < 0) return fail(ABB_ERR_ARG, "negative query count");
     if (!(spec->direction & 3)) return fail(ABB_ERR_ARG, "direction must be forward, reverse or both");
@@ -415,28 +472,98 @@ static int enqueue_walk(abb_graph *g, const abb_walk_spec *spec, const abb_walk_
     if ((fl & ABB_WALK_EDGES) && (!io->q_estart || !io->q_ecount || (!io->edges && io->edge_cap > 0))) return fail(ABB_ERR_ARG, "EDGES needs edge outputs");
     if ((fl & ABB_WALK_HIST) && !io->q_hist) return fail(ABB_ERR_ARG, "HIST needs io.q_hist");
     if ((fl & ABB_WALK_TARGET) && !io->targets) return fail(ABB_ERR_ARG, "TARGET needs io.targets");
+    return ABB_OK;
+}
+
+struct HeadToI64 { __host__ __device__ int64_t operator()(uint8_t v) const { return static_cast<int64_t>(v); } };
+
+// Group single-source walks by their level-1 frontier, walk each group once, share the slice (dedup.cuh).
+static int enqueue_dedup_walk(abb_graph *g, const abb_walk_spec *spec, const abb_walk_io *io, cudaStream_t st) {
+    const int64_t nq = io->n_queries;
+    const size_t q1 = static_cast<size_t>(nq) + 2;
+    const uint32_t fl = spec->flags;
+    int rc = ABB_OK;
+#define ENS(buf, bytes) if (!rc) rc = g->buf.ensure(bytes)
+    ENS(dd_sig, q1 * 8); ENS(dd_ssig, q1 * 8); ENS(dd_q, q1 * 4); ENS(dd_sq, q1 * 4); ENS(dd_head, q1); ENS(dd_gid, q1 * 8); ENS(dd_hp, q1 * 8);
+    ENS(dd_glen, q1 * 8); ENS(dd_goff, q1 * 8); ENS(dd_arena, q1 * 4 * L1_CAP); ENS(dd_memoff, q1 * 8); ENS(dd_memsrc, q1 * 4); ENS(dd_memstate, q1 * 4);
+    ENS(dd_indiv, q1 * 4); ENS(dd_cnt, 8 * sizeof(unsigned long long));
+    ENS(dd_gstart, q1 * 8); ENS(dd_gcount, q1 * 4); ENS(dd_gmaxd, q1 * 4); ENS(dd_gflags, q1 * 4);
+    if (fl & ABB_WALK_HIST) { ENS(dd_ghist, q1 * ABB_N_ENTITY_TYPES * 4); }
+#undef ENS
+    if (rc) return rc;
+    unsigned long long *cnt = g->dd_cnt.as<unsigned long long>();
+    unsigned long long *sig = g->dd_sig.as<unsigned long long>(), *ssig = g->dd_ssig.as<unsigned long long>();
+    int32_t *qi = g->dd_q.as<int32_t>(), *sq = g->dd_sq.as<int32_t>(), *indiv = g->dd_indiv.as<int32_t>();
+    uint8_t *head = g->dd_head.as<uint8_t>();
+    int64_t *gid = g->dd_gid.as<int64_t>(), *hp = g->dd_hp.as<int64_t>(), *glen = g->dd_glen.as<int64_t>(), *goff = g->dd_goff.as<int64_t>();
+    int64_t *memoff = g->dd_memoff.as<int64_t>();
+    const unsigned blocks = static_cast<unsigned>((nq + 255) / 256);
+    CUDA_TRY(cudaMemsetAsync(cnt, 0, 8 * sizeof(unsigned long long), st));
+    CUDA_TRY(cudaMemsetAsync(glen, 0, q1 * 8, st));
+    dedup_sig_kernel<<<blocks, 256, 0, st>>>(g->v, *spec, io->roots, nq, sig, qi); g_launches++;
+    // temp storage: the largest of the cub calls below
+    size_t t_sort = 0, t_scan = 0, t_sel = 0, t_scan2 = 0;
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, t_sort, sig, ssig, qi, sq, static_cast<int>(nq), 0, 64, st));
+    cub::TransformInputIterator<int64_t, HeadToI64, const uint8_t *> head64(head, HeadToI64());
+    CUDA_TRY(cub::DeviceScan::InclusiveSum(nullptr, t_scan, head64, gid, static_cast<int>(nq), st));
+    cub::CountingInputIterator<int64_t> iota(0);
+    CUDA_TRY(cub::DeviceSelect::Flagged(nullptr, t_sel, iota, head, hp, cnt, static_cast<int>(nq), st));
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, t_scan2, glen, goff, static_cast<int>(nq + 1), st));
+    size_t tmp = std::max(std::max(t_sort, t_scan), std::max(t_sel, t_scan2)) + 256;
+    if ((rc = g->dd_tmp.ensure(tmp))) return rc;
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(g->dd_tmp.p, t_sort, sig, ssig, qi, sq, static_cast<int>(nq), 0, 64, st)); g_launches++;
+    dedup_heads_kernel<<<blocks, 256, 0, st>>>(ssig, sq, nq, head, indiv, cnt); g_launches++;
+    CUDA_TRY(cub::DeviceScan::InclusiveSum(g->dd_tmp.p, t_scan, head64, gid, static_cast<int>(nq), st)); g_launches++;
+    CUDA_TRY(cub::DeviceSelect::Flagged(g->dd_tmp.p, t_sel, iota, head, hp, cnt, static_cast<int>(nq), st)); g_launches++;
+    dedup_groups_kernel<<<static_cast<unsigned>((nq + 1 + 255) / 256), 256, 0, st>>>(g->v, *spec, io->roots, sq, hp, cnt, glen, memoff); g_launches++;
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(g->dd_tmp.p, t_scan2, glen, goff, static_cast<int>(nq + 1), st)); g_launches++;
+    dedup_roots_kernel<<<blocks, 256, 0, st>>>(g->v, *spec, io->roots, sq, hp, cnt, goff, g->dd_arena.as<int32_t>()); g_launches++;
+    dedup_members_kernel<<<blocks, 256, 0, st>>>(g->v, *spec, io->roots, sq, head, gid, goff, g->dd_arena.as<int32_t>(), g->dd_memsrc.as<int32_t>(),
+                                                  g->dd_memstate.as<int32_t>(), indiv, cnt); g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    unsigned long long *ctl = g->ctl.as<unsigned long long>();
+    // canonical walks: one per group, seeded with the shared frontier, one level shallower, depths biased by one
+    WalkArgs C{};
+    C.g = g->v; C.spec = *spec; C.io = *io;
+    C.spec.max_depth = spec->max_depth < 0 ? -1 : spec->max_depth - 1;
+    C.spec.flags = (fl & ~(ABB_WALK_OMIT_ROOTS | ABB_WALK_REAL_ROOTS)) | ABB_WALK_MARK_ROOTS;
+    C.io.roots = g->dd_arena.as<int32_t>(); C.io.root_off = goff;
+    C.io.q_start = g->dd_gstart.as<int64_t>(); C.io.q_count = g->dd_gcount.as<int32_t>(); C.io.q_maxd = g->dd_gmaxd.as<int32_t>();
+    C.io.q_flags = g->dd_gflags.as<int32_t>(); C.io.q_hist = g->dd_ghist.as<uint32_t>();
+    C.qlist = nullptr; C.nq = 0; C.nq_dev = cnt;
+    C.depth_bias = 1; C.hist_roots = 1;
+    C.mem_off = memoff; C.mem_src = g->dd_memsrc.as<int32_t>(); C.mem_state = g->dd_memstate.as<int32_t>();
+    if ((rc = enqueue_tiers(g, C, nq, ctl, g->ov1.as<int32_t>(), g->ov2.as<int32_t>(), st))) return rc;
+    dedup_share_kernel<<<static_cast<unsigned>(std::min<int64_t>((nq + 255) / 256, static_cast<int64_t>(g->sm_count) * 8)), 256, 0, st>>>(
+        sq, gid, g->dd_memstate.as<int32_t>(), cnt, C.io.q_start, C.io.q_count, C.io.q_maxd, C.io.q_flags, C.io.q_hist, io->q_start, io->q_count, io->q_maxd,
+        io->q_flags, (fl & ABB_WALK_HIST) ? io->q_hist : nullptr, indiv, cnt);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    // individual walks: ineligible sources, signature collisions, sources reached by their own group's walk
+    WalkArgs I{};
+    I.g = g->v; I.spec = *spec; I.io = *io;
+    I.qlist = indiv; I.nq = 0; I.nq_dev = cnt + 1;
+    return enqueue_tiers(g, I, nq, ctl + 16, g->ov1.as<int32_t>(), g->ov2.as<int32_t>(), st);
+}
+
+static bool dedup_applies(const abb_graph *g, const abb_walk_spec *spec, const abb_walk_io *io) {
+    const uint32_t fl = spec->flags;
+    return g->dedup_enabled && !io->root_off && io->n_queries >= 256 && (fl & ABB_WALK_MARK_ROOTS) && (fl & ABB_WALK_OMIT_ROOTS) &&
+           !(fl & (ABB_WALK_TARGET | ABB_WALK_EDGES | ABB_WALK_PARENTS)) && spec->max_nodes < 0 && spec->max_edges < 0 && spec->max_depth != 0;
+}
+
+static int enqueue_walk(abb_graph *g, const abb_walk_spec *spec, const abb_walk_io *io, cudaStream_t st) {
+    if (int rc = check_walk_io(spec, io)) return rc;
     CUDA_TRY(cudaMemsetAsync(io->totals, 0, 2 * sizeof(unsigned long long), st));
     if (io->n_queries == 0) return ABB_OK;
     if (int rc = g->ov1.ensure(static_cast<size_t>(io->n_queries) * 4)) return rc;
     if (int rc = g->ov2.ensure(static_cast<size_t>(io->n_queries) * 4)) return rc;
-    CUDA_TRY(cudaMemsetAsync(g->ctl.p, 0, 16 * sizeof(unsigned long long), st));
-    const bool par = fl & ABB_WALK_PARENTS;
-    const bool meta = spec->rel_mask != 0xFFFFFFFFu || (fl & ABB_WALK_TRAVERSABLE_ONLY);
-    const bool bud = spec->max_nodes >= 0 || spec->max_edges >= 0;
-    unsigned long long *ctl = g->ctl.as<unsigned long long>();
+    CUDA_TRY(cudaMemsetAsync(g->ctl.p, 0, 64 * sizeof(unsigned long long), st));
+    if (dedup_applies(g, spec, io)) return enqueue_dedup_walk(g, spec, io, st);
     WalkArgs A{};
     A.g = g->v; A.spec = *spec; A.io = *io;
-    // tier S1: every query
-    A.qlist = nullptr; A.nq = io->n_queries; A.nq_dev = nullptr; A.ctl = ctl; A.overflow = g->ov1.as<int32_t>();
-    if (int rc = launch_smem_variant<S1_H, S1_Q, S1_WARPS>(g, A, io->n_queries, par, meta, bud, st)) return rc;
-    // tier S2: queries that outgrew S1 (count = ctl[1])
-    A.qlist = g->ov1.as<int32_t>(); A.nq = 0; A.nq_dev = ctl + 1; A.ctl = ctl + 4; A.overflow = g->ov2.as<int32_t>();
-    if (int rc = launch_smem_variant<S2_H, S2_Q, S2_WARPS>(g, A, static_cast<int64_t>(g->sm_count) * 2 * WORK_CHUNK, par, meta, bud, st)) return rc;
-    // tier G: queries that outgrew S2 (count = ctl[5])
-    A.qlist = g->ov2.as<int32_t>(); A.nq = 0; A.nq_dev = ctl + 5; A.ctl = ctl + 8; A.overflow = nullptr;
-    A.g_bitmap = g->g_bitmap.as<uint32_t>(); A.g_queue = g->g_queue.as<int32_t>(); A.g_par = g->g_par.as<int32_t>(); A.g_dep = g->g_dep.as<int32_t>();
-    A.g_words = g->g_words; A.g_qcap = g->g_qcap;
-    return launch_global_variant(g, A, meta, bud, st);
+    A.qlist = nullptr; A.nq = io->n_queries; A.nq_dev = nullptr;
+    return enqueue_tiers(g, A, io->n_queries, g->ctl.as<unsigned long long>(), g->ov1.as<int32_t>(), g->ov2.as<int32_t>(), st);
 }
 
 extern "C" int abb_walk_launch(abb_graph *g, const abb_walk_spec *spec, const abb_walk_io *io, void *stream) {
@@ -542,9 +669,10 @@ static int walk_device_stage(abb_graph *g, const abb_walk_spec *spec, const int3
         g->walk_timed = true;
         CUDA_TRY(cudaMemcpyAsync(totals, g->d_totals.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
-        unsigned long long fatal = 0;
+        unsigned long long fatal = 0, fatal2 = 0;
         CUDA_TRY(cudaMemcpy(&fatal, g->ctl.as<unsigned long long>() + 10, sizeof fatal, cudaMemcpyDeviceToHost));
-        if (fatal) return fail(ABB_ERR_CAPACITY, "a traversal outgrew the global scratch tier (more than n_nodes+4096 queue entries)");
+        CUDA_TRY(cudaMemcpy(&fatal2, g->ctl.as<unsigned long long>() + 26, sizeof fatal2, cudaMemcpyDeviceToHost));
+        if (fatal || fatal2) return fail(ABB_ERR_CAPACITY, "a traversal outgrew the global scratch tier (more than n_nodes+4096 queue entries)");
         *io_out = io;
         const bool fits = static_cast<int64_t>(totals[0]) <= node_cap && (!(fl & ABB_WALK_EDGES) || static_cast<int64_t>(totals[1]) <= edge_cap);
         g->hint_nodes = std::max<int64_t>(g->hint_nodes, static_cast<int64_t>(totals[0]));
@@ -601,13 +729,29 @@ extern "C" int abb_walk_host(abb_graph *g, const abb_walk_spec *spec, const int3
 }
 
 // ------------------------------------------------------------------ exposure-path rows
+static int ensure_server_table(abb_graph *g, cudaStream_t st) {
+    if (g->srv_table_ready) return ABB_OK;
+    const size_t n = static_cast<size_t>(g->v.n) + 1;
+    if (int rc = g->srv_cred.ensure(n * 4)) return rc;
+    if (int rc = g->srv_tool.ensure(n * 4)) return rc;
+    const int64_t blocks = std::min<int64_t>((g->v.n + 255) / 256, static_cast<int64_t>(g->sm_count) * 16);
+    server_table_kernel<<<static_cast<unsigned>(std::max<int64_t>(1, blocks)), 256, 0, st>>>(g->v, g->srv_cred.as<int32_t>(), g->srv_tool.as<int32_t>());
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(st));   // one-time: later launches may come on other streams
+    g->srv_table_ready = true;
+    return ABB_OK;
+}
+
 static int enqueue_paths_count(abb_graph *g, const abb_paths_io *io, cudaStream_t st) {
     if (!io || io->n_findings < 0 || !io->f_off || (io->n_findings && !io->findings)) return fail(ABB_ERR_ARG, "bad paths io");
+    if (int rc = ensure_server_table(g, st)) return rc;
     const int64_t nf = io->n_findings;
     if (int rc = g->p_counts.ensure(static_cast<size_t>(nf + 1) * 8)) return rc;
     CUDA_TRY(cudaMemsetAsync(g->p_counts.p, 0, static_cast<size_t>(nf + 1) * 8, st));
     if (nf) {
         PathsArgs A{}; A.g = g->v; A.io = *io; A.counts = g->p_counts.as<int64_t>();
+        A.srv_cred = g->srv_cred.as<int32_t>(); A.srv_tool = g->srv_tool.as<int32_t>();
         int64_t blocks = std::min<int64_t>((nf + 7) / 8, static_cast<int64_t>(g->sm_count) * 8);
         paths_kernel<false><<<static_cast<unsigned>(std::max<int64_t>(1, blocks)), 256, 0, st>>>(A);
         g_launches++;
@@ -624,7 +768,9 @@ static int enqueue_paths_count(abb_graph *g, const abb_paths_io *io, cudaStream_
 static int enqueue_paths_fill(abb_graph *g, const abb_paths_io *io, cudaStream_t st) {
     if (!io || !io->f_off || !io->hops || !io->rels || !io->ncred || !io->ntool) return fail(ABB_ERR_ARG, "bad paths io");
     if (!io->n_findings) return ABB_OK;
+    if (int rc = ensure_server_table(g, st)) return rc;
     PathsArgs A{}; A.g = g->v; A.io = *io; A.counts = nullptr;
+    A.srv_cred = g->srv_cred.as<int32_t>(); A.srv_tool = g->srv_tool.as<int32_t>();
     int64_t blocks = std::min<int64_t>((io->n_findings + 7) / 8, static_cast<int64_t>(g->sm_count) * 8);
     paths_kernel<true><<<static_cast<unsigned>(std::max<int64_t>(1, blocks)), 256, 0, st>>>(A);
     g_launches++;

@@ -50,6 +50,13 @@ struct WalkArgs {
     // tier G scratch (per warp slot)
     uint32_t *g_bitmap; int32_t *g_queue; int32_t *g_par; int32_t *g_dep;
     int64_t g_words, g_qcap;
+    // canonical (root-frontier de-duplicated) mode: a query is a GROUP of sources that share their level-1 frontier,
+    // seeded with that frontier; depths are offset by one and every member source is tested against the visited set
+    int32_t depth_bias;          // added to emitted depths / max depth (1 in canonical mode)
+    int32_t hist_roots;          // count the seeded roots in the histogram too
+    const int64_t *mem_off;      // [groups+1] member range of each group in the sorted member arrays (NULL = not canonical)
+    const int32_t *mem_src;      // source node of each member
+    int32_t *mem_state;          // set to 2 when the member's own source was reached (its result differs: traversed individually)
 };
 
 __device__ __forceinline__ unsigned lanemask_lt(int lane) { return (1u << lane) - 1u; }
@@ -245,7 +252,7 @@ __device__ bool walk_one(const WalkArgs &A, Store &st, int64_t q, int lane) {
     const int32_t target = (fl & ABB_WALK_TARGET) ? __ldg(io.targets + q) : -1;
 
     idx_t lvl_begin = 0, lvl_end = tail, exp_end = 0;
-    int depth = 0, maxd = 0;
+    int depth = 0, maxd = n_roots ? A.depth_bias : 0;
     long long rec_edges = 0;      // passing candidates recorded (== edge_count while under budget)
     bool stop = false;
 
@@ -308,7 +315,7 @@ __device__ bool walk_one(const WalkArgs &A, Store &st, int64_t q, int lane) {
         }
         depth++;
         lvl_begin = lvl_end; lvl_end = tail;
-        if (lvl_end > lvl_begin) maxd = depth;
+        if (lvl_end > lvl_begin) maxd = depth + A.depth_bias;
     }
 
     // ---- emit the slice: reserve a contiguous range, then copy (optionally type-filtered)
@@ -342,12 +349,12 @@ __device__ bool walk_one(const WalkArgs &A, Store &st, int64_t q, int lane) {
                 unsigned long long pos = w + __popc(okm & lanemask_lt(lane));
                 io.nodes[pos] = node;
                 if (fl & ABB_WALK_PARENTS) io.parent[pos] = st.par_get(k);
-                if (fl & ABB_WALK_DEPTHS) io.depth[pos] = st.dep_get(k);
+                if (fl & ABB_WALK_DEPTHS) io.depth[pos] = st.dep_get(k) + A.depth_bias;
             }
             w += __popc(okm);
             if (fl & ABB_WALK_HIST) {
                 // roots are never counted (impact_of excludes the source, container.py:265)
-                bool hv = ok && k >= n_roots && t < ABB_N_ENTITY_TYPES;
+                bool hv = ok && (k >= n_roots || A.hist_roots) && t < ABB_N_ENTITY_TYPES;
 #pragma unroll
                 for (int b = 0; b < ABB_N_ENTITY_TYPES; b++) {
                     unsigned bm = __ballot_sync(FULL, hv && t == b);
@@ -382,6 +389,12 @@ __device__ bool walk_one(const WalkArgs &A, Store &st, int64_t q, int lane) {
         }
     }
 
+    // canonical mode: a member whose own source was reached would not list it -> mark it for an individual traversal
+    if (A.mem_off) {
+        const int64_t m0 = A.mem_off[q], m1 = A.mem_off[q + 1];
+        for (int64_t m = m0 + lane; m < m1; m += 32)
+            if (A.mem_state[m] == 0 && st.contains(__ldg(A.mem_src + m))) A.mem_state[m] = 2;
+    }
     if (lane == 0) {
         io.q_start[q] = static_cast<int64_t>(start);
         io.q_count[q] = static_cast<int32_t>(count);

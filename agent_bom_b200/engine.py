@@ -140,6 +140,10 @@ class DeviceGraph:
             raise RuntimeError("DeviceGraph is closed")
         return self._h
 
+    def set_dedup(self, enabled: bool) -> None:
+        """Toggle root-frontier de-duplication of single-source batches (results are identical either way)."""
+        _lib.check(_lib.load().abb_graph_set_dedup(self.handle, int(bool(enabled))))
+
     @property
     def nbytes(self) -> int:
         return int(_lib.load().abb_graph_bytes(self.handle))

@@ -70,7 +70,7 @@ SEVERITY_RANK = {
 # Adjacency-entry meta byte layout (device format)
 META_REL_MASK = 0x1F
 META_TRAVERSABLE = 0x20
-META_BIDIRECTIONAL = 0x40
+META_FIRST_PAIR = 0x40
 META_REVERSED_COPY = 0x80
 
 ALL_RELS_MASK = 0xFFFFFFFF

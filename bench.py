@@ -196,7 +196,7 @@ def main() -> int:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="L", choices=sorted(WORKLOADS))
     ap.add_argument("--seed", type=int, default=2145)
-    ap.add_argument("--batch", type=int, default=1 << 17, help="findings per launch batch")
+    ap.add_argument("--batch", type=int, default=1 << 22, help="findings per launch batch (one batch de-duplicates shared frontiers best)")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work per CPU-baseline pass")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--check", type=int, default=2000, help="findings spot-checked against the oracle before timing")

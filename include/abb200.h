@@ -39,7 +39,7 @@ typedef enum abb_status {
 /* adjacency-entry meta byte (device format) */
 #define ABB_META_REL_MASK 0x1Fu
 #define ABB_META_TRAVERSABLE 0x20u
-#define ABB_META_BIDIRECTIONAL 0x40u
+#define ABB_META_FIRST_PAIR 0x40u   /* first entry of its row with this neighbour (set by the CSR build) */
 #define ABB_META_REVERSED_COPY 0x80u
 /* per-edge input flags of the edge stream */
 #define ABB_EDGE_TRAVERSABLE 1u
@@ -62,7 +62,11 @@ int abb_device_count(void);
  * (graph.edges order) contributes (row=src,nbr=dst,eid2=2i) forward and
  * (row=dst,nbr=src,eid2=2i) reverse; a bidirectional edge also contributes
  * its reversed copy (row=dst,nbr=src,eid2=2i+1) forward and
- * (row=src,nbr=dst,eid2=2i+1) reverse.
+ * (row=src,nbr=dst,eid2=2i+1) reverse.  meta = rel(5 bits) | TRAVERSABLE |
+ * FIRST_PAIR | REVERSED_COPY.  Entries of adjacency[a] with neighbour b and
+ * entries of reverse_adjacency[b] with neighbour a correspond one-to-one in the
+ * same order, so FIRST_PAIR on either side marks the edge whose relationship
+ * the reference's by_pair.setdefault((a,b)) keeps (api/routes/graph.py:492-497).
  * ---------------------------------------------------------------------- */
 typedef struct abb_csr {
     int32_t n_nodes;          /* real nodes + ghosts */
@@ -97,6 +101,10 @@ int abb_graph_adopt(int device, const abb_csr *dev, abb_graph **out);
 /* device pointers of a graph (for broadcast / inspection) */
 int abb_graph_view(const abb_graph *g, abb_csr *out);
 int64_t abb_graph_bytes(const abb_graph *g);
+/* Root-frontier de-duplication of single-source batches (on by default; env ABB_DEDUP=0 disables at creation).
+ * Sources whose depth-1 frontier is identical share one traversal and one result slice; results are
+ * bit-identical either way (q_start of different queries may then alias the same arena range). */
+int abb_graph_set_dedup(abb_graph *g, int enabled);
 int abb_graph_device(const abb_graph *g);
 void abb_graph_free(abb_graph *g);
 

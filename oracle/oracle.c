@@ -30,7 +30,7 @@
  *   (row=dst, nbr=src, eid2=2i) to rev; a bidirectional edge additionally
  *   contributes its reversed copy (row=dst, nbr=src, eid2=2i+1) to fwd and
  *   (row=src, nbr=dst, eid2=2i+1) to rev.  meta byte = rel(5b) | traversable<<5
- *   | bidirectional<<6 | reversed_copy<<7.  node_type[u] = entity code, 255 for
+ *   | first_pair<<6 (unused by the oracle) | reversed_copy<<7.  node_type[u] = entity code, 255 for
  *   an id that appears only as an edge endpoint ("ghost": not in graph.nodes).
  *
  * Sources are independent, so the *_many functions run them on all host
@@ -45,7 +45,7 @@
 
 #define META_REL 0x1F
 #define META_TRAV 0x20
-#define META_BIDIR 0x40
+#define META_FIRSTPAIR 0x40
 #define META_REVCOPY 0x80
 #define GHOST 255
 #define NHIST 24

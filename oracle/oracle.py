@@ -22,7 +22,7 @@ import numpy as np
 HERE = Path(__file__).resolve().parent
 LIB_PATH = HERE / "liboracle.so"
 
-META_TRAV, META_BIDIR, META_REVCOPY = 0x20, 0x40, 0x80
+META_TRAV, META_FIRSTPAIR, META_REVCOPY = 0x20, 0x40, 0x80
 FLAG_TRAVERSABLE, FLAG_BIDIRECTIONAL = 1, 2
 GHOST = 255
 NHIST = 24
@@ -142,7 +142,7 @@ def build_csr(n_nodes: int, src, dst, rel, flags, node_type) -> OracleGraph:
     ne = src.shape[0]
     idx = np.arange(ne, dtype=np.int64)
     bid = (flags & FLAG_BIDIRECTIONAL) != 0
-    base_meta = (rel & 0x1F) | np.where(flags & FLAG_TRAVERSABLE, META_TRAV, 0).astype(np.uint8) | np.where(bid, META_BIDIR, 0).astype(np.uint8)
+    base_meta = (rel & 0x1F) | np.where(flags & FLAG_TRAVERSABLE, META_TRAV, 0).astype(np.uint8)
     bidx = idx[bid]
     # forward: original under source, reversed copy under target (right after the original in insertion time)
     f_row = np.concatenate([src, dst[bid]])
@@ -158,11 +158,22 @@ def build_csr(n_nodes: int, src, dst, rel, flags, node_type) -> OracleGraph:
     rp, r_off = _stable_rows(r_row, r_key, n_nodes)
     nt = np.ascontiguousarray(node_type, dtype=np.uint8)
     assert nt.shape[0] == n_nodes
+
+    def first_pair(off, nbr_sorted, meta_sorted):
+        # first entry of each row with a given neighbour (graph.py:492-497 keeps that edge's relationship for the pair)
+        row = np.repeat(np.arange(n_nodes, dtype=np.int64), np.diff(off.astype(np.int64)))
+        _, first = np.unique(row * n_nodes + nbr_sorted.astype(np.int64), return_index=True)
+        out = meta_sorted.copy()
+        out[first] |= META_FIRSTPAIR
+        return out
+
+    f_meta_sorted = first_pair(f_off, f_nbr[fp], f_meta[fp])
+    r_meta_sorted = first_pair(r_off, r_nbr[rp], r_meta[rp])
     return OracleGraph(
         n_nodes=n_nodes,
-        fwd_off=f_off, fwd_nbr=np.ascontiguousarray(f_nbr[fp], dtype=np.int32), fwd_meta=np.ascontiguousarray(f_meta[fp]),
+        fwd_off=f_off, fwd_nbr=np.ascontiguousarray(f_nbr[fp], dtype=np.int32), fwd_meta=np.ascontiguousarray(f_meta_sorted),
         fwd_eid=np.ascontiguousarray(f_key[fp], dtype=np.uint32),
-        rev_off=r_off, rev_nbr=np.ascontiguousarray(r_nbr[rp], dtype=np.int32), rev_meta=np.ascontiguousarray(r_meta[rp]),
+        rev_off=r_off, rev_nbr=np.ascontiguousarray(r_nbr[rp], dtype=np.int32), rev_meta=np.ascontiguousarray(r_meta_sorted),
         rev_eid=np.ascontiguousarray(r_key[rp], dtype=np.uint32),
         node_type=nt,
     )

@@ -73,9 +73,11 @@ def test_csr_build_matches_oracle_model():
             np.testing.assert_array_equal(getattr(h, name), getattr(og, name), err_msg=name)
 
 
+@pytest.mark.parametrize("dedup", [True, False])
 @pytest.mark.parametrize("key", SEEDED + ["estate_150", "estate_dense_40"])
-def test_impact_many(key):
+def test_impact_many(key, dedup):
     og, dg, nt, _, _ = graphs_for(key)
+    dg.set_dedup(dedup)
     rng = np.random.default_rng(7)
     n = og.n_nodes
     sources = np.concatenate([rng.integers(0, n, size=min(4000, 4 * n)), np.arange(min(n, 64)), [-1, n + 3]]).astype(np.int32)
@@ -86,6 +88,7 @@ def test_impact_many(key):
         np.testing.assert_array_equal(got.maxd, want.maxd)
         np.testing.assert_array_equal(got.hist, want.hist)
         np.testing.assert_array_equal(got.flags & 2, want.flags & 2)
+    dg.set_dedup(True)
 
 
 @pytest.mark.parametrize("key", SEEDED + ["estate_150", "estate_dense_40"])
@@ -110,10 +113,12 @@ def test_reachable_from(key):
         assert_slices_equal(dg.reachable_many(sources, depth, trav), orc.reachable_many(og, sources, depth, trav))
 
 
+@pytest.mark.parametrize("dedup", [True, False])
 @pytest.mark.parametrize("key", SEEDED + ["estate_150", "estate_dense_40"])
-def test_distances_unbounded_masked(key):
+def test_distances_unbounded_masked(key, dedup):
     """_bfs_distances_along: unbounded depth — on the big seeded graphs this exercises the overflow tiers."""
     og, dg, _, _, _ = graphs_for(key)
+    dg.set_dedup(dedup)
     rng = np.random.default_rng(17)
     sources = rng.integers(0, og.n_nodes, size=300).astype(np.int32)
     for mask in (REACH4, 0xFFFFFFFF, LATERAL | REACH4):
