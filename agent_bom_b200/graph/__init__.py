@@ -1,0 +1,19 @@
+"""Typed exposure graph — the Python surface of the reference's ``agent_bom.graph`` for the traversal hot path.
+
+    from agent_bom_b200.graph import UnifiedGraph, UnifiedNode, UnifiedEdge, EntityType, RelationshipType, AttackPath
+    from agent_bom_b200.graph import compute_dependency_reach, derived_attack_paths
+
+Mirrors ``/root/reference/src/agent_bom/graph/__init__.py:8-100`` for the names the hot path needs.
+"""
+
+from .container import UnifiedGraph
+from .dependency_reach import PackageReachability, ReachabilityReport, VulnerabilityReachability, compute_dependency_reach
+from .exposure import derived_attack_paths, exposure_path_rows, materialize_attack_paths, node_risk_100
+from .model import AttackPath, UnifiedEdge, UnifiedNode
+from .schema import FINDING_ENTITY_TYPES, SEVERITY_RANK, EntityType, NodeStatus, RelationshipType
+
+__all__ = [
+    "AttackPath", "EntityType", "FINDING_ENTITY_TYPES", "NodeStatus", "PackageReachability", "ReachabilityReport", "RelationshipType", "SEVERITY_RANK",
+    "UnifiedEdge", "UnifiedGraph", "UnifiedNode", "VulnerabilityReachability", "compute_dependency_reach", "derived_attack_paths", "exposure_path_rows",
+    "materialize_attack_paths", "node_risk_100",
+]

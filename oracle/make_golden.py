@@ -335,7 +335,31 @@ def run_battery(name: str, g: UnifiedGraph, rng: random.Random, small: bool, der
     print(f"{name}: {ix.n_real} nodes (+{len(ids) - ix.n_real} ghosts) {len(edges)} edges, {len(findings)} findings -> {path.name} {path.stat().st_size / 1024:.0f} KiB")
 
 
+def estate_identity():
+    """Pin agent_bom_b200.estate: its direct-to-arrays graph must equal what the reference builder makes of its report JSON."""
+    from agent_bom_b200 import estate as est_mod
+
+    docs = []
+    for agents, knobs, label in ((150, est_mod.Knobs(), "shipped-shape"), (60, est_mod.Knobs.dense(6, 8, 3), "dense-6-8-3"), (90, est_mod.BENCH_KNOBS, "bench-knobs")):
+        est = est_mod.generate(agents, 2145, knobs, exact_rank=True)
+        g = build_unified_graph_from_report(est.report_json())
+        ix = Indexer(g)
+        node_types, edges, _, _ = graph_arrays(g, ix)
+        docs.append({"label": label, "agents": agents, "seed": 2145, "knobs": dict(knobs.__dict__), "node_ids": ix.ids, "node_types": node_types, "edges": edges,
+                     "node_severity": [n.severity for n in g.nodes.values()], "node_labels": [n.label for n in g.nodes.values()]})
+        print(f"estate_identity {label}: {len(ix.ids)} nodes {len(edges)} edges")
+    path = OUT / "identity" / "estate_identity.json.gz"
+    path.parent.mkdir(parents=True, exist_ok=True)
+    with gzip.GzipFile(path, "wb", mtime=0) as fh:
+        fh.write(json.dumps(docs, separators=(",", ":"), sort_keys=True).encode())
+    print(f"-> {path} {path.stat().st_size / 1024:.0f} KiB")
+
+
 def main():
+    if "--identity-only" in sys.argv:
+        estate_identity()
+        return
+    estate_identity()
     rng = random.Random(20260921)
     run_battery("kat_schema", kat_schema(), rng, small=True)
     run_battery("kat_directed", kat_directed(), rng, small=True)

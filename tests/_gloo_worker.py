@@ -1,0 +1,32 @@
+"""Worker of tests/test_host_api.py::test_gloo_world2_broadcast_and_shard (launched by torch.distributed.run, backend gloo)."""
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+
+import numpy as np  # noqa: E402
+
+from agent_bom_b200 import dist as abdist  # noqa: E402
+from agent_bom_b200 import estate  # noqa: E402
+from agent_bom_b200.graph import csr as csrmod  # noqa: E402
+
+info = abdist.init_from_env("gloo")
+est = estate.generate(60, 7, estate.Knobs.dense(4, 8, 2))
+ref = csrmod.from_arrays(None, est.node_type, est.src, est.dst, est.rel, est.flags, node_rank=est.node_rank)
+host = ref if info.rank == 0 else None
+findings = est.findings if info.rank == 0 else None
+tensors, n, m = abdist.broadcast_csr(host, info, "cpu")
+f = abdist.broadcast_array(findings, info, "cpu")
+assert (n, m) == (ref.n_nodes, ref.n_entries)
+for name in abdist.CSR_FIELDS:
+    want = getattr(ref, name)
+    want = want.view(np.int32) if want.dtype == np.uint32 else want
+    assert np.array_equal(tensors[name].numpy(), want), name
+assert np.array_equal(f.numpy(), est.findings)
+lo, hi = abdist.shard_bounds(len(f), info.world, info.rank)
+assert int(abdist.sum_over_ranks(hi - lo, info, "cpu")) == len(f)
+assert abdist.max_over_ranks(float(info.rank), info, "cpu") == float(info.world - 1)
+abdist.barrier(info)
+sys.stdout.write("rank%d-ok\n" % info.rank)
+sys.stdout.flush()

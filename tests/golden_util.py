@@ -121,3 +121,19 @@ def rank_path_rows(doc: dict, rows, g) -> list[dict]:
         })
     out.sort(key=lambda p: (p["risk"], len(p["hops"]), len(p["creds"]), len(p["tools"])), reverse=True)
     return out
+
+
+def graph_from_fixture(doc: dict):
+    """Our host container rebuilt from a golden fixture (string ids, labels, severities, risk scores)."""
+    from agent_bom_b200.graph import EntityType, RelationshipType, UnifiedEdge, UnifiedGraph, UnifiedNode
+    from agent_bom_b200.graph.schema import ENTITY_VALUES, RELATIONSHIP_VALUES
+
+    g = UnifiedGraph(scan_id="golden", tenant_id="t")
+    ids = doc["node_ids"]
+    for i in range(doc["n_real"]):
+        g.add_node(UnifiedNode(id=ids[i], entity_type=EntityType(ENTITY_VALUES[doc["node_types"][i]]), label=doc["node_labels"][i],
+                               risk_score=doc["node_risk"][i], severity=doc["node_severity"][i]))
+    for s, t, r, fl in doc["edges"]:
+        g.add_edge(UnifiedEdge(source=ids[s], target=ids[t], relationship=RelationshipType(RELATIONSHIP_VALUES[r]) if r < 31 else "custom",
+                               direction="bidirectional" if fl & 2 else "directed", traversable=bool(fl & 1)))
+    return g
