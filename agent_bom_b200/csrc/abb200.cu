@@ -192,6 +192,10 @@ struct abb_graph {
     bool srv_table_ready = false;
     // paths staging
     DevBuf p_findings, p_counts, p_off, p_hops, p_rels, p_ncred, p_ntool, p_scan_tmp;
+    // exposure-path pipeline workspace (links, templates)
+    DevBuf pl_cnt, pl_off, pl_vs, pl_rel, pl_rows, pl_roff, pl_need, pl_ulist, pl_nu, pt_cnt, pt_off, pt_off_node, pt_cnt_node, pt_row, pt_rel;
+    PathsArgs paths_args{};
+    bool paths_args_valid = false;
     int64_t hint_rows = 0;
     // owned graph arrays
     std::vector<void *> owned_ptrs;
@@ -212,9 +216,10 @@ static int graph_finish_init(abb_graph *g) {
     if (int rc = g->ctl.ensure(64 * sizeof(unsigned long long))) return rc;
     const int64_t n = g->v.n;
     g->g_words = (n + 31) / 32 + 1;
-    // tier G1: 8 warps per SM, queue bounded at 64K entries (or the whole graph if smaller)
+    // tier G1: 24 warps per SM (latency-bound pointer chasing wants every warp it can get), queue bounded at 64K entries
     g->g_qcap = std::min<int64_t>(n + 4096, 1 << 16);
-    g->g_slots = g->sm_count * 8;
+    g->g_slots = g->sm_count * 24;
+    if (const char *e = getenv("ABB_G1_WARPS_PER_SM")) g->g_slots = g->sm_count * std::max(4, std::min(32, atoi(e)));
     {
         const size_t sl = static_cast<size_t>(g->g_slots);
         if (int rc = g->g_bitmap.ensure(sl * g->g_words * 4)) return rc;
@@ -334,7 +339,7 @@ extern "C" void abb_graph_free(abb_graph *g) {
     for (DevBuf *b : {&g->ctl, &g->ov1, &g->ov2, &g->g_bitmap, &g->g_queue, &g->g_par, &g->g_dep, &g->x_bitmap, &g->x_queue, &g->x_par, &g->x_dep, &g->dd_sig, &g->dd_ssig, &g->dd_q, &g->dd_sq, &g->dd_head, &g->dd_gid, &g->dd_hp, &g->dd_glen, &g->dd_goff, &g->dd_arena, &g->dd_memoff, &g->dd_memsrc, &g->dd_memstate, &g->dd_indiv, &g->dd_cnt, &g->dd_tmp, &g->dd_gstart, &g->dd_gcount, &g->dd_gmaxd, &g->dd_gflags, &g->dd_ghist, &g->identity_rank, &g->d_roots, &g->d_root_off,
                       &g->d_targets, &g->d_qstart, &g->d_qcount, &g->d_qmaxd, &g->d_qflags, &g->d_qestart, &g->d_qecount, &g->d_qhist, &g->d_nodes,
                       &g->d_parent, &g->d_depth, &g->d_edges, &g->d_totals, &g->p_findings, &g->p_counts, &g->p_off, &g->p_hops, &g->p_rels,
-                      &g->p_ncred, &g->p_ntool, &g->p_scan_tmp, &g->srv_cred, &g->srv_tool})
+                      &g->p_ncred, &g->p_ntool, &g->p_scan_tmp, &g->srv_cred, &g->srv_tool, &g->pl_cnt, &g->pl_off, &g->pl_vs, &g->pl_rel, &g->pl_rows, &g->pl_roff, &g->pl_need, &g->pl_ulist, &g->pl_nu, &g->pt_cnt, &g->pt_off, &g->pt_off_node, &g->pt_cnt_node, &g->pt_row, &g->pt_rel})
         b->release();
     if (g->owned) for (void *p : g->owned_ptrs) cudaFree(p);
     delete g;
@@ -439,7 +444,7 @@ static int launch_global_variant(const WalkArgs &A, int slots, bool meta, bool b
 // Three tiers on one stream.  `A` carries spec/io and the first tier's work list (qlist/nq/nq_dev); every later
 // tier reads its work list and count from device memory, so nothing here waits for the GPU.
 //   S1  warp + shared-memory hash/queue            (<= 512 queue entries)
-//   G1  warp + global bitmap, bounded queue slot   (<= 64K queue entries), 8 warps per SM
+//   G1  warp + global bitmap, bounded queue slot   (<= 64K queue entries), 24 warps per SM
 //   GX  warp + global bitmap, whole-graph slot     (anything)
 // ctl: 12 counters — tier t uses ctl[4t .. 4t+3] = {work cursor, overflow count, fatal flag, -}
 static int enqueue_tiers(abb_graph *g, WalkArgs A, int64_t max_items, unsigned long long *ctl, int32_t *ov1, int32_t *ov2, cudaStream_t st) {
@@ -743,36 +748,90 @@ static int ensure_server_table(abb_graph *g, cudaStream_t st) {
     return ABB_OK;
 }
 
+static int scan_i64(abb_graph *g, const int64_t *in, int64_t *out, int64_t n, cudaStream_t st) {
+    size_t tmp = 0;
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, out, static_cast<int>(n), st));
+    if (int rc = g->p_scan_tmp.ensure(tmp + 16)) return rc;
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(g->p_scan_tmp.p, tmp, in, out, static_cast<int>(n), st));
+    g_launches++;
+    return ABB_OK;
+}
+
+static unsigned warp_grid(const abb_graph *g, int64_t warps) {
+    return static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>((warps + 7) / 8, static_cast<int64_t>(g->sm_count) * 8)));
+}
+
+// Count pass of the exposure-path pipeline (paths.cuh): links -> unique vulnerable sources -> templates -> per-finding
+// row offsets.  Synchronises the stream twice to size the link / template buffers.
 static int enqueue_paths_count(abb_graph *g, const abb_paths_io *io, cudaStream_t st) {
     if (!io || io->n_findings < 0 || !io->f_off || (io->n_findings && !io->findings)) return fail(ABB_ERR_ARG, "bad paths io");
+    if (io->n_findings >= (1ll << 31) - 2) return fail(ABB_ERR_ARG, "too many findings in one batch");
     if (int rc = ensure_server_table(g, st)) return rc;
-    const int64_t nf = io->n_findings;
-    if (int rc = g->p_counts.ensure(static_cast<size_t>(nf + 1) * 8)) return rc;
-    CUDA_TRY(cudaMemsetAsync(g->p_counts.p, 0, static_cast<size_t>(nf + 1) * 8, st));
-    if (nf) {
-        PathsArgs A{}; A.g = g->v; A.io = *io; A.counts = g->p_counts.as<int64_t>();
-        A.srv_cred = g->srv_cred.as<int32_t>(); A.srv_tool = g->srv_tool.as<int32_t>();
-        int64_t blocks = std::min<int64_t>((nf + 7) / 8, static_cast<int64_t>(g->sm_count) * 8);
-        paths_kernel<false><<<static_cast<unsigned>(std::max<int64_t>(1, blocks)), 256, 0, st>>>(A);
+    g->paths_args_valid = false;
+    const int64_t nf = io->n_findings, n = g->v.n;
+    PathsArgs A{};
+    A.g = g->v; A.io = *io; A.srv_cred = g->srv_cred.as<int32_t>(); A.srv_tool = g->srv_tool.as<int32_t>();
+    int rc = ABB_OK;
+#define ENS(buf, bytes) if (!rc) rc = g->buf.ensure(static_cast<size_t>(bytes))
+    ENS(pl_cnt, (nf + 2) * 8); ENS(pl_off, (nf + 2) * 8); ENS(pl_need, n + 16); ENS(pl_ulist, (n + 2) * 4); ENS(pl_nu, 16);
+    ENS(pt_off_node, (n + 2) * 8); ENS(pt_cnt_node, (n + 2) * 4);
+    if (rc) return rc;
+    A.link_cnt = g->pl_cnt.as<int64_t>(); A.link_off = g->pl_off.as<int64_t>(); A.need = g->pl_need.as<uint8_t>();
+    A.ulist = g->pl_ulist.as<int32_t>(); A.n_unique = g->pl_nu.as<unsigned long long>();
+    A.t_off_node = g->pt_off_node.as<int64_t>(); A.t_cnt_node = g->pt_cnt_node.as<int32_t>();
+    A.n_links = reinterpret_cast<const unsigned long long *>(A.link_off + nf);
+    CUDA_TRY(cudaMemsetAsync(A.link_cnt, 0, static_cast<size_t>(nf + 2) * 8, st));
+    if (nf) { links_kernel<false><<<warp_grid(g, nf), 256, 0, st>>>(A); g_launches++; }
+    if ((rc = scan_i64(g, A.link_cnt, A.link_off, nf + 1, st))) return rc;
+    int64_t NL = 0;
+    CUDA_TRY(cudaMemcpyAsync(&NL, A.link_off + nf, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    const int64_t nu_max = std::min<int64_t>(NL, n);
+    ENS(pl_vs, (NL + 2) * 4); ENS(pl_rel, NL + 16); ENS(pl_rows, (NL + 2) * 8); ENS(pl_roff, (NL + 2) * 8); ENS(pt_cnt, (nu_max + 2) * 8); ENS(pt_off, (nu_max + 2) * 8);
+    if (rc) return rc;
+    A.link_vs = g->pl_vs.as<int32_t>(); A.link_rel = g->pl_rel.as<int8_t>(); A.link_rows = g->pl_rows.as<int64_t>(); A.link_roff = g->pl_roff.as<int64_t>();
+    A.t_cnt = g->pt_cnt.as<int64_t>(); A.t_off = g->pt_off.as<int64_t>();
+    CUDA_TRY(cudaMemsetAsync(A.need, 0, static_cast<size_t>(n) + 16, st));
+    if (nf) { links_kernel<true><<<warp_grid(g, nf), 256, 0, st>>>(A); g_launches++; }
+    // unique vulnerable sources, node order
+    {
+        cub::CountingInputIterator<int32_t> iota(0);
+        size_t tmp = 0;
+        CUDA_TRY(cub::DeviceSelect::Flagged(nullptr, tmp, iota, A.need, g->pl_ulist.as<int32_t>(), g->pl_nu.as<unsigned long long>(), static_cast<int>(n), st));
+        if ((rc = g->p_scan_tmp.ensure(tmp + 16))) return rc;
+        CUDA_TRY(cub::DeviceSelect::Flagged(g->p_scan_tmp.p, tmp, iota, A.need, g->pl_ulist.as<int32_t>(), g->pl_nu.as<unsigned long long>(), static_cast<int>(n), st));
         g_launches++;
-        CUDA_TRY(cudaGetLastError());
     }
-    size_t tmp = 0;
-    CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp, g->p_counts.as<int64_t>(), io->f_off, static_cast<int>(nf + 1), st));
-    if (int rc = g->p_scan_tmp.ensure(tmp + 16)) return rc;
-    CUDA_TRY(cub::DeviceScan::ExclusiveSum(g->p_scan_tmp.p, tmp, g->p_counts.as<int64_t>(), io->f_off, static_cast<int>(nf + 1), st));
-    g_launches++;
+    CUDA_TRY(cudaMemsetAsync(A.t_cnt, 0, static_cast<size_t>(nu_max + 2) * 8, st));
+    if (nu_max) { template_kernel<false><<<warp_grid(g, nu_max), 256, 0, st>>>(A); g_launches++; }
+    if ((rc = scan_i64(g, A.t_cnt, A.t_off, nu_max + 1, st))) return rc;
+    int64_t TR = 0;
+    CUDA_TRY(cudaMemcpyAsync(&TR, A.t_off + nu_max, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    ENS(pt_row, (TR + 2) * 16); ENS(pt_rel, (TR + 2) * 2);
+    if (rc) return rc;
+#undef ENS
+    A.t_row = g->pt_row.as<int4>(); A.t_rel = g->pt_rel.as<int8_t>();
+    if (nu_max) { template_kernel<true><<<warp_grid(g, nu_max), 256, 0, st>>>(A); g_launches++; }
+    CUDA_TRY(cudaMemsetAsync(A.link_rows, 0, static_cast<size_t>(NL + 2) * 8, st));
+    if (NL) { link_rows_kernel<<<static_cast<unsigned>((NL + 255) / 256), 256, 0, st>>>(A); g_launches++; }
+    if ((rc = scan_i64(g, A.link_rows, A.link_roff, NL + 1, st))) return rc;
+    finding_offsets_kernel<<<static_cast<unsigned>((nf + 1 + 255) / 256), 256, 0, st>>>(A); g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    g->paths_args = A;
+    g->paths_args_valid = true;
     return ABB_OK;
 }
 
 static int enqueue_paths_fill(abb_graph *g, const abb_paths_io *io, cudaStream_t st) {
     if (!io || !io->f_off || !io->hops || !io->rels || !io->ncred || !io->ntool) return fail(ABB_ERR_ARG, "bad paths io");
     if (!io->n_findings) return ABB_OK;
-    if (int rc = ensure_server_table(g, st)) return rc;
-    PathsArgs A{}; A.g = g->v; A.io = *io; A.counts = nullptr;
-    A.srv_cred = g->srv_cred.as<int32_t>(); A.srv_tool = g->srv_tool.as<int32_t>();
-    int64_t blocks = std::min<int64_t>((io->n_findings + 7) / 8, static_cast<int64_t>(g->sm_count) * 8);
-    paths_kernel<true><<<static_cast<unsigned>(std::max<int64_t>(1, blocks)), 256, 0, st>>>(A);
+    if (!g->paths_args_valid || g->paths_args.io.findings != io->findings || g->paths_args.io.n_findings != io->n_findings || g->paths_args.io.f_off != io->f_off)
+        return fail(ABB_ERR_ARG, "abb_paths_fill_launch must follow abb_paths_count_launch for the same findings / f_off");
+    if ((reinterpret_cast<uintptr_t>(io->hops) & 15) != 0 || (reinterpret_cast<uintptr_t>(io->rels) & 3) != 0) return fail(ABB_ERR_ARG, "io.hops must be 16-byte and io.rels 4-byte aligned");
+    PathsArgs A = g->paths_args;
+    A.io = *io;
+    replicate_kernel<<<warp_grid(g, (io->n_findings + 31) / 32), 256, 0, st>>>(A);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return ABB_OK;
@@ -837,7 +896,7 @@ static int paths_run(abb_graph *g, const int32_t *h_findings, const int32_t *d_f
     r->rows = total;
     const size_t rows = static_cast<size_t>(total);
     int rc = g->p_hops.ensure(rows * 16 + 16);
-    if (!rc) rc = g->p_rels.ensure(rows * 3 + 16);
+    if (!rc) rc = g->p_rels.ensure(rows * 4 + 16);
     if (!rc) rc = g->p_ncred.ensure(rows * 4 + 16);
     if (!rc) rc = g->p_ntool.ensure(rows * 4 + 16);
     if (rc) { delete r; return rc; }
@@ -846,16 +905,16 @@ static int paths_run(abb_graph *g, const int32_t *h_findings, const int32_t *d_f
     if (rc) { delete r; return rc; }
     CUDA_TRY(cudaEventRecord(g->ev[3], st));
     g->paths_timed = true;
-    bool ok = r->off.alloc(static_cast<size_t>(nf + 1) * 8) && r->hops.alloc(rows * 16) && r->rels.alloc(rows * 3) && r->ncred.alloc(rows * 4) && r->ntool.alloc(rows * 4);
+    bool ok = r->off.alloc(static_cast<size_t>(nf + 1) * 8) && r->hops.alloc(rows * 16) && r->rels.alloc(rows * 4) && r->ncred.alloc(rows * 4) && r->ntool.alloc(rows * 4);
     if (!ok) { abb_paths_result_free(r); return fail(ABB_ERR_NOMEM, "pinned host allocation failed"); }
     cudaError_t e = cudaMemcpyAsync(r->off.p, io.f_off, static_cast<size_t>(nf + 1) * 8, cudaMemcpyDeviceToHost, st);
     if (rows && e == cudaSuccess) e = cudaMemcpyAsync(r->hops.p, io.hops, rows * 16, cudaMemcpyDeviceToHost, st);
-    if (rows && e == cudaSuccess) e = cudaMemcpyAsync(r->rels.p, io.rels, rows * 3, cudaMemcpyDeviceToHost, st);
+    if (rows && e == cudaSuccess) e = cudaMemcpyAsync(r->rels.p, io.rels, rows * 4, cudaMemcpyDeviceToHost, st);
     if (rows && e == cudaSuccess) e = cudaMemcpyAsync(r->ncred.p, io.ncred, rows * 4, cudaMemcpyDeviceToHost, st);
     if (rows && e == cudaSuccess) e = cudaMemcpyAsync(r->ntool.p, io.ntool, rows * 4, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { abb_paths_result_free(r); return fail(ABB_ERR_CUDA, "paths D2H failed: %s", cudaGetErrorString(e)); }
-    r->d2h = static_cast<int64_t>((nf + 1) * 8 + rows * 27);
+    r->d2h = static_cast<int64_t>((nf + 1) * 8 + rows * 28);
     *out = r;
     return ABB_OK;
 }

@@ -38,9 +38,26 @@ constexpr uint32_t LONG_ROW = 64;   // reverse rows of a server longer than this
 struct PathsArgs {
     GraphView g;
     abb_paths_io io;
-    int64_t *counts;            // [n_findings] per-finding row counts (pass 1 output)
     const int32_t *srv_cred;    // [n_nodes] EXPOSES_CRED fan-out of server nodes (graph-constant table)
     const int32_t *srv_tool;    // [n_nodes] PROVIDES_TOOL fan-out
+    // links: one per (finding, vulnerable source) in emission order
+    int64_t *link_cnt;          // [n_findings+1] links per finding (count pass), then scanned into link_off
+    int64_t *link_off;          // [n_findings+1]
+    int32_t *link_vs;           // [n_links]
+    int8_t *link_rel;           // [n_links] relationship of the pair (vs, finding)
+    int64_t *link_rows;         // [n_links+1] rows per link, scanned into link_roff
+    int64_t *link_roff;         // [n_links+1]
+    const unsigned long long *n_links;   // device scalar
+    // templates: the rows of one vulnerable source, shared by every finding attached to it
+    uint8_t *need;              // [n_nodes] vs is referenced by some link
+    const int32_t *ulist;       // [n_unique] vulnerable sources, node order
+    const unsigned long long *n_unique;  // device scalar
+    int64_t *t_cnt;             // [n_unique+1] rows per template, scanned into t_off
+    int64_t *t_off;             // [n_unique+1]
+    int64_t *t_off_node;        // [n_nodes] template offset by vs node
+    int32_t *t_cnt_node;        // [n_nodes] template length by vs node
+    int4 *t_row;                // [n_template_rows] agent, server, ncred, ntool
+    int8_t *t_rel;              // [n_template_rows*2] (agent,server) and (server,vs) relationships
 };
 
 // graph-constant table: credential / tool fan-out of every server (originals only, target must have a node record)
@@ -116,14 +133,10 @@ __device__ __forceinline__ bool next_agent_warp(const GraphView &g, int32_t s, i
     return true;
 }
 
-__device__ __forceinline__ void write_row(const PathsArgs &A, int64_t row, int32_t agent, int32_t srv, int32_t vs, int32_t f, int rel_as, int rel_sv, int rel_vf) {
-    int32_t *h = A.io.hops + row * 4;
-    h[0] = agent; h[1] = srv; h[2] = (vs != srv) ? vs : -1; h[3] = f;
-    int8_t *r = A.io.rels + row * 3;
-    if (vs != srv) { r[0] = static_cast<int8_t>(rel_as); r[1] = static_cast<int8_t>(rel_sv); r[2] = static_cast<int8_t>(rel_vf); }
-    else { r[0] = static_cast<int8_t>(rel_as); r[1] = static_cast<int8_t>(rel_vf); r[2] = -2; }
-    A.io.ncred[row] = __ldg(A.srv_cred + srv);
-    A.io.ntool[row] = __ldg(A.srv_tool + srv);
+// one template row: (agent, server) and the relationships of the pairs (agent,server), (server,vs)
+__device__ __forceinline__ void write_row(const PathsArgs &A, int64_t row, int32_t agent, int32_t srv, int32_t, int32_t, int rel_as, int rel_sv, int) {
+    A.t_row[row] = make_int4(agent, srv, __ldg(A.srv_cred + srv), __ldg(A.srv_tool + srv));
+    A.t_rel[row * 2] = static_cast<int8_t>(rel_as); A.t_rel[row * 2 + 1] = static_cast<int8_t>(rel_sv);
 }
 
 // Rows of up to 32 candidate servers (lane i owns server s, -1 = none) of one (finding, vulnerable source).
@@ -173,59 +186,135 @@ __device__ int64_t server_chunk(const PathsArgs &A, int64_t row0, int32_t s, int
     return total;
 }
 
+// ---- pass A: links of every finding (VULNERABLE_TO originals whose source has a node record), in row order
 template <bool FILL>
-__global__ void __launch_bounds__(256) paths_kernel(const PathsArgs A) {
+__global__ void __launch_bounds__(256) links_kernel(const PathsArgs A) {
     const GraphView &g = A.g;
     const int lane = threadIdx.x & 31;
     const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
     for (int64_t fi = warp; fi < A.io.n_findings; fi += nwarps) {
         const int32_t f = __ldg(A.io.findings + fi);
-        int64_t row = FILL ? A.io.f_off[fi] : 0, n = 0;
+        int64_t n = 0;
+        const int64_t base = FILL ? A.link_off[fi] : 0;
         bool ok = f >= 0 && f < g.n;
         if (ok) { const uint8_t ft = __ldg(g.ntype + f); ok = ft == ET_VULN || ft == ET_MISCONF; }
         if (ok) {
             const uint32_t s0 = __ldg(g.roff + f), e0 = __ldg(g.roff + f + 1);
             for (uint32_t p = s0; p < e0; p += 32) {
                 const uint32_t k = p + lane;
-                int32_t vs = -1; int vt = 0, rvf = -1;
+                int32_t vs = -1; int rvf = -1;
                 if (k < e0) {
                     const uint32_t m = __ldg(g.rmeta + k);
                     if (!(m & ABB_META_REVERSED_COPY) && (m & ABB_META_REL_MASK) == REL_VULNERABLE_TO) {
                         const int32_t v = __ldg(g.rnbr + k);
-                        vt = __ldg(g.ntype + v);
-                        if (vt != ABB_NODE_GHOST) { vs = v; rvf = (m & ABB_META_FIRST_PAIR) ? REL_VULNERABLE_TO : -3; }
+                        if (__ldg(g.ntype + v) != ABB_NODE_GHOST) { vs = v; rvf = (m & ABB_META_FIRST_PAIR) ? REL_VULNERABLE_TO : -3; }
                     }
                 }
-                unsigned vm = __ballot_sync(FULL, vs >= 0);
-                while (vm) {  // vulnerable sources in row order
-                    const int src = __ffs(vm) - 1; vm &= vm - 1;
-                    const int32_t cvs = __shfl_sync(FULL, vs, src);
-                    const int cvt = __shfl_sync(FULL, vt, src);
-                    int rel_vf = __shfl_sync(FULL, rvf, src);
-                    if (FILL && rel_vf == -3) rel_vf = first_rel_rev(g, cvs, f);
-                    if (cvt == ET_SERVER) {
-                        n += server_chunk<FILL>(A, row + n, lane == 0 ? cvs : -1, -2, cvs, f, rel_vf, lane);
-                    } else {
-                        const uint32_t s2 = __ldg(g.roff + cvs), e2 = __ldg(g.roff + cvs + 1);
-                        for (uint32_t p2 = s2; p2 < e2; p2 += 32) {
-                            const uint32_t k2 = p2 + lane;
-                            int32_t srv = -1; int rsv = -1;
-                            if (k2 < e2) {
-                                const uint32_t m2 = __ldg(g.rmeta + k2);
-                                if (!(m2 & ABB_META_REVERSED_COPY) && (m2 & ABB_META_REL_MASK) == REL_DEPENDS_ON) {
-                                    const int32_t v2 = __ldg(g.rnbr + k2);
-                                    if (__ldg(g.ntype + v2) == ET_SERVER) { srv = v2; rsv = (m2 & ABB_META_FIRST_PAIR) ? REL_DEPENDS_ON : -3; }
-                                }
-                            }
-                            if (FILL && rsv == -3) rsv = first_rel_rev(g, srv, cvs);
-                            if (__any_sync(FULL, srv >= 0)) n += server_chunk<FILL>(A, row + n, srv, rsv, cvs, f, rel_vf, lane);
-                        }
-                    }
+                const unsigned vm = __ballot_sync(FULL, vs >= 0);
+                if (FILL && vs >= 0) {
+                    if (rvf == -3) rvf = first_rel_rev(g, vs, f);
+                    const int64_t o = base + n + __popc(vm & lanemask_lt(lane));
+                    A.link_vs[o] = vs; A.link_rel[o] = static_cast<int8_t>(rvf);
+                    A.need[vs] = 1;
                 }
+                n += __popc(vm);
             }
         }
-        if (!FILL && lane == 0) A.counts[fi] = n;
+        if (!FILL && lane == 0) A.link_cnt[fi] = n;
+    }
+}
+
+// ---- pass B: the template of each referenced vulnerable source (count, then fill)
+template <bool FILL>
+__global__ void __launch_bounds__(256) template_kernel(const PathsArgs A) {
+    const GraphView &g = A.g;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    const int64_t nu = static_cast<int64_t>(*A.n_unique);
+    for (int64_t ui = warp; ui < nu; ui += nwarps) {
+        const int32_t vs = __ldg(A.ulist + ui);
+        const int64_t row = FILL ? A.t_off[ui] : 0;
+        int64_t n = 0;
+        if (__ldg(g.ntype + vs) == ET_SERVER) {
+            n += server_chunk<FILL>(A, row, lane == 0 ? vs : -1, -2, vs, 0, 0, lane);
+        } else {
+            const uint32_t s2 = __ldg(g.roff + vs), e2 = __ldg(g.roff + vs + 1);
+            for (uint32_t p2 = s2; p2 < e2; p2 += 32) {
+                const uint32_t k2 = p2 + lane;
+                int32_t srv = -1; int rsv = -1;
+                if (k2 < e2) {
+                    const uint32_t m2 = __ldg(g.rmeta + k2);
+                    if (!(m2 & ABB_META_REVERSED_COPY) && (m2 & ABB_META_REL_MASK) == REL_DEPENDS_ON) {
+                        const int32_t v2 = __ldg(g.rnbr + k2);
+                        if (__ldg(g.ntype + v2) == ET_SERVER) { srv = v2; rsv = (m2 & ABB_META_FIRST_PAIR) ? REL_DEPENDS_ON : -3; }
+                    }
+                }
+                if (FILL && rsv == -3) rsv = first_rel_rev(g, srv, vs);
+                if (__any_sync(FULL, srv >= 0)) n += server_chunk<FILL>(A, row + n, srv, rsv, vs, 0, 0, lane);
+            }
+        }
+        if (lane == 0) {
+            if (!FILL) { A.t_cnt[ui] = n; A.t_cnt_node[vs] = static_cast<int32_t>(n); }
+            else A.t_off_node[vs] = row;
+        }
+    }
+}
+
+__global__ void link_rows_kernel(const PathsArgs A) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < static_cast<int64_t>(*A.n_links)) A.link_rows[i] = A.t_cnt_node[A.link_vs[i]];
+}
+
+__global__ void finding_offsets_kernel(const PathsArgs A) {
+    const int64_t fi = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (fi <= A.io.n_findings) A.io.f_off[fi] = A.link_roff[A.link_off[fi]];
+}
+
+// ---- pass C: every link copies its vulnerable source's template, substituting the finding
+__device__ __forceinline__ void emit_row(const PathsArgs &A, int64_t out, int64_t t, int32_t vs, int32_t f, int rel_vf) {
+    const int4 tr = A.t_row[t];
+    const int32_t srv = tr.y;
+    const int ras = A.t_rel[t * 2], rsv = A.t_rel[t * 2 + 1];
+    reinterpret_cast<int4 *>(A.io.hops)[out] = make_int4(tr.x, srv, (vs != srv) ? vs : -1, f);
+    // rels are stored 4 bytes per row (the 4th is padding) so a row's relationships are one aligned word
+    const uint32_t packed = (vs != srv) ? ((ras & 0xFF) | ((rsv & 0xFF) << 8) | ((rel_vf & 0xFF) << 16) | (0xFEu << 24))
+                                        : ((ras & 0xFF) | ((rel_vf & 0xFF) << 8) | (0xFEu << 16) | (0xFEu << 24));
+    reinterpret_cast<uint32_t *>(A.io.rels)[out] = packed;
+    A.io.ncred[out] = tr.z;
+    A.io.ntool[out] = tr.w;
+}
+
+__global__ void __launch_bounds__(256) replicate_kernel(const PathsArgs A) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    const int64_t nf = A.io.n_findings;
+    // a warp takes 32 findings; short links are copied lane-serially, long ones by the whole warp
+    for (int64_t fb = warp * 32; fb < nf; fb += nwarps * 32) {
+        const int64_t fi = fb + lane;
+        int64_t l0 = 0, l1 = 0; int32_t f = 0;
+        if (fi < nf) { l0 = A.link_off[fi]; l1 = A.link_off[fi + 1]; f = __ldg(A.io.findings + fi); }
+        for (int64_t l = l0; l < l1; l++) {
+            const int64_t rows = A.link_roff[l + 1] - A.link_roff[l];
+            if (rows > 8) continue;                 // long links below
+            const int32_t vs = A.link_vs[l]; const int rel = A.link_rel[l];
+            const int64_t t0 = A.t_off_node[vs], o0 = A.link_roff[l];
+            for (int64_t k = 0; k < rows; k++) emit_row(A, o0 + k, t0 + k, vs, f, rel);
+        }
+        // long links: lane j announces them one at a time, the warp streams the template 32 rows per step
+        for (int j = 0; j < 32; j++) {
+            const int64_t jl0 = __shfl_sync(FULL, l0, j), jl1 = __shfl_sync(FULL, l1, j);
+            const int32_t jf = __shfl_sync(FULL, f, j);
+            for (int64_t l = jl0; l < jl1; l++) {
+                const int64_t o0 = A.link_roff[l], rows = A.link_roff[l + 1] - o0;
+                if (rows <= 8) continue;
+                const int32_t vs = A.link_vs[l]; const int rel = A.link_rel[l];
+                const int64_t t0 = A.t_off_node[vs];
+                for (int64_t k = lane; k < rows; k += 32) emit_row(A, o0 + k, t0 + k, vs, jf, rel);
+            }
+        }
     }
 }
 

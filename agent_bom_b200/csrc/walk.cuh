@@ -247,6 +247,19 @@ __device__ bool walk_one(const WalkArgs &A, Store &st, int64_t q, int lane) {
         __syncwarp();
     }
     const idx_t n_roots = tail;
+    if (!Store::kGlobal && n_roots > 0 && n_roots <= 32 && (sp.max_depth < 0 || sp.max_depth > 0)) {
+        // cheap size forecast: if the roots alone have more candidates than this tier's queue holds, the walk will
+        // almost surely outgrow it — hand it to the next tier now instead of after filling the queue
+        uint32_t deg = 0;
+        if (lane < n_roots) {
+            const int32_t r = st.q_get(lane);
+            if (sp.direction & 1) deg += __ldg(g.foff + r + 1) - __ldg(g.foff + r);
+            if (sp.direction & 2) deg += __ldg(g.roff + r + 1) - __ldg(g.roff + r);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) deg += __shfl_xor_sync(FULL, deg, o);
+        if (deg > static_cast<uint32_t>(st.qcap())) { st.clear(tail, lane); return false; }
+    }
     int qflags = 0;
     if (n_roots == 0) qflags |= ABB_QFLAG_NO_ROOT;
     const int32_t target = (fl & ABB_WALK_TARGET) ? __ldg(io.targets + q) : -1;

@@ -239,7 +239,7 @@ class DeviceGraph:
         rows = int(lib.abb_paths_result_rows(res))
         return PathRows(
             off=_view(lib.abb_paths_result_off(res), nf + 1, np.int64), hops=_view(lib.abb_paths_result_hops(res), rows * 4, np.int32).reshape(rows, 4),
-            rels=_view(lib.abb_paths_result_rels(res), rows * 3, np.int8).reshape(rows, 3), ncred=_view(lib.abb_paths_result_ncred(res), rows, np.int32),
+            rels=np.ascontiguousarray(_view(lib.abb_paths_result_rels(res), rows * 4, np.int8).reshape(rows, 4)[:, :3]), ncred=_view(lib.abb_paths_result_ncred(res), rows, np.int32),
             ntool=_view(lib.abb_paths_result_ntool(res), rows, np.int32),
             h2d_bytes=int(lib.abb_paths_result_h2d_bytes(res)), d2h_bytes=int(lib.abb_paths_result_d2h_bytes(res)),
         )

@@ -105,7 +105,7 @@ class DevicePaths:
             dev = self.f_off.device
             self.row_cap = int(row_cap)
             self.hops = torch.empty(self.row_cap * 4, dtype=torch.int32, device=dev)
-            self.rels = torch.empty(self.row_cap * 3, dtype=torch.int8, device=dev)
+            self.rels = torch.empty(self.row_cap * 4, dtype=torch.int8, device=dev)   # 4 bytes per row: 3 relationships + pad
             self.ncred = torch.empty(self.row_cap, dtype=torch.int32, device=dev)
             self.ntool = torch.empty(self.row_cap, dtype=torch.int32, device=dev)
 

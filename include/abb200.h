@@ -234,16 +234,16 @@ void abb_walk_result_free(abb_walk_result *r);
  * agents sorted by node_rank).  Risk scoring and the final stable sort
  * (:762-786) need Python floats and are done by the host layer.
  *   hops [n_paths*4] : agent, server, vulnerable_source (-1 when it is the server), finding
- *   rels [n_paths*3] : relationship code per consecutive hop pair; -1 = the pair
- *                      has no edge (the reference skips it); -2 = not applicable
+ *   rels [n_paths*4] : relationship code per consecutive hop pair (3 used, the 4th byte pads the row to one
+ *                      aligned word); -1 = the pair has no edge (the reference skips it); -2 = not applicable
  *   ncred/ntool      : EXPOSES_CRED / PROVIDES_TOOL out-edges of the server (un-deduplicated)
  * ---------------------------------------------------------------------- */
 typedef struct abb_paths_io {
     int64_t n_findings;
     const int32_t *findings;  /* device [n_findings] */
     int64_t *f_off;           /* device [n_findings+1] exclusive scan of per-finding path counts */
-    int32_t *hops;            /* device [row_cap*4] */
-    int8_t *rels;             /* device [row_cap*3] */
+    int32_t *hops;            /* device [row_cap*4], 16-byte aligned */
+    int8_t *rels;             /* device [row_cap*4], 4-byte aligned */
     int32_t *ncred;           /* device [row_cap] */
     int32_t *ntool;           /* device [row_cap] */
     int64_t row_cap;
