@@ -109,6 +109,15 @@ EXPORTS = {
     "abb_paths_fill_launch": (C.c_int, [vp, C.POINTER(PathsIO), vp]),
     "abb_paths_host": (C.c_int, [vp, vp, i64, C.POINTER(vp)]),
     "abb_paths_result_rows": (i64, [vp]),
+    "abb_paths_result_links": (i64, [vp]),
+    "abb_paths_result_template_rows": (i64, [vp]),
+    "abb_paths_result_link_off": (vp, [vp]),
+    "abb_paths_result_link_source": (vp, [vp]),
+    "abb_paths_result_link_rel": (vp, [vp]),
+    "abb_paths_result_link_row_off": (vp, [vp]),
+    "abb_paths_result_link_template": (vp, [vp]),
+    "abb_paths_result_template": (vp, [vp]),
+    "abb_paths_result_template_rel": (vp, [vp]),
     "abb_paths_result_off": (vp, [vp]),
     "abb_paths_result_hops": (vp, [vp]),
     "abb_paths_result_rels": (vp, [vp]),

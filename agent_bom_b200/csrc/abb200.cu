@@ -12,6 +12,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cub/cub.cuh>
@@ -193,9 +194,10 @@ struct abb_graph {
     // paths staging
     DevBuf p_findings, p_counts, p_off, p_hops, p_rels, p_ncred, p_ntool, p_scan_tmp;
     // exposure-path pipeline workspace (links, templates)
-    DevBuf pl_cnt, pl_off, pl_vs, pl_rel, pl_rows, pl_roff, pl_need, pl_ulist, pl_nu, pt_cnt, pt_off, pt_off_node, pt_cnt_node, pt_row, pt_rel;
+    DevBuf pl_cnt, pl_off, pl_vs, pl_rel, pl_rows, pl_roff, pl_toff, pl_need, pl_ulist, pl_nu, pt_cnt, pt_off, pt_off_node, pt_cnt_node, pt_row, pt_rel;
     PathsArgs paths_args{};
     bool paths_args_valid = false;
+    int64_t paths_n_links = 0, paths_n_template_rows = 0;
     int64_t hint_rows = 0;
     // owned graph arrays
     std::vector<void *> owned_ptrs;
@@ -339,7 +341,7 @@ extern "C" void abb_graph_free(abb_graph *g) {
     for (DevBuf *b : {&g->ctl, &g->ov1, &g->ov2, &g->g_bitmap, &g->g_queue, &g->g_par, &g->g_dep, &g->x_bitmap, &g->x_queue, &g->x_par, &g->x_dep, &g->dd_sig, &g->dd_ssig, &g->dd_q, &g->dd_sq, &g->dd_head, &g->dd_gid, &g->dd_hp, &g->dd_glen, &g->dd_goff, &g->dd_arena, &g->dd_memoff, &g->dd_memsrc, &g->dd_memstate, &g->dd_indiv, &g->dd_cnt, &g->dd_tmp, &g->dd_gstart, &g->dd_gcount, &g->dd_gmaxd, &g->dd_gflags, &g->dd_ghist, &g->identity_rank, &g->d_roots, &g->d_root_off,
                       &g->d_targets, &g->d_qstart, &g->d_qcount, &g->d_qmaxd, &g->d_qflags, &g->d_qestart, &g->d_qecount, &g->d_qhist, &g->d_nodes,
                       &g->d_parent, &g->d_depth, &g->d_edges, &g->d_totals, &g->p_findings, &g->p_counts, &g->p_off, &g->p_hops, &g->p_rels,
-                      &g->p_ncred, &g->p_ntool, &g->p_scan_tmp, &g->srv_cred, &g->srv_tool, &g->pl_cnt, &g->pl_off, &g->pl_vs, &g->pl_rel, &g->pl_rows, &g->pl_roff, &g->pl_need, &g->pl_ulist, &g->pl_nu, &g->pt_cnt, &g->pt_off, &g->pt_off_node, &g->pt_cnt_node, &g->pt_row, &g->pt_rel})
+                      &g->p_ncred, &g->p_ntool, &g->p_scan_tmp, &g->srv_cred, &g->srv_tool, &g->pl_cnt, &g->pl_off, &g->pl_vs, &g->pl_rel, &g->pl_rows, &g->pl_roff, &g->pl_toff, &g->pl_need, &g->pl_ulist, &g->pl_nu, &g->pt_cnt, &g->pt_off, &g->pt_off_node, &g->pt_cnt_node, &g->pt_row, &g->pt_rel})
         b->release();
     if (g->owned) for (void *p : g->owned_ptrs) cudaFree(p);
     delete g;
@@ -787,9 +789,9 @@ static int enqueue_paths_count(abb_graph *g, const abb_paths_io *io, cudaStream_
     CUDA_TRY(cudaMemcpyAsync(&NL, A.link_off + nf, 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     const int64_t nu_max = std::min<int64_t>(NL, n);
-    ENS(pl_vs, (NL + 2) * 4); ENS(pl_rel, NL + 16); ENS(pl_rows, (NL + 2) * 8); ENS(pl_roff, (NL + 2) * 8); ENS(pt_cnt, (nu_max + 2) * 8); ENS(pt_off, (nu_max + 2) * 8);
+    ENS(pl_vs, (NL + 2) * 4); ENS(pl_rel, NL + 16); ENS(pl_rows, (NL + 2) * 8); ENS(pl_roff, (NL + 2) * 8); ENS(pl_toff, (NL + 2) * 8); ENS(pt_cnt, (nu_max + 2) * 8); ENS(pt_off, (nu_max + 2) * 8);
     if (rc) return rc;
-    A.link_vs = g->pl_vs.as<int32_t>(); A.link_rel = g->pl_rel.as<int8_t>(); A.link_rows = g->pl_rows.as<int64_t>(); A.link_roff = g->pl_roff.as<int64_t>();
+    A.link_vs = g->pl_vs.as<int32_t>(); A.link_rel = g->pl_rel.as<int8_t>(); A.link_rows = g->pl_rows.as<int64_t>(); A.link_roff = g->pl_roff.as<int64_t>(); A.link_toff = g->pl_toff.as<int64_t>();
     A.t_cnt = g->pt_cnt.as<int64_t>(); A.t_off = g->pt_off.as<int64_t>();
     CUDA_TRY(cudaMemsetAsync(A.need, 0, static_cast<size_t>(n) + 16, st));
     if (nf) { links_kernel<true><<<warp_grid(g, nf), 256, 0, st>>>(A); g_launches++; }
@@ -820,6 +822,7 @@ static int enqueue_paths_count(abb_graph *g, const abb_paths_io *io, cudaStream_
     CUDA_TRY(cudaGetLastError());
     g->paths_args = A;
     g->paths_args_valid = true;
+    g->paths_n_links = NL; g->paths_n_template_rows = TR;
     return ABB_OK;
 }
 
@@ -857,21 +860,79 @@ extern "C" int abb_paths_fill_launch(abb_graph *g, const abb_paths_io *io, void 
     return ABB_OK;
 }
 
+// Host result of the exposure-path pipeline.  What crosses PCIe is the FACTORISED form — per finding its links
+// (vulnerable source + relationship), per link the template slice of that source — which determines every row;
+// the flat row arrays of the ABI are expanded from it on the host, on first access.
 struct abb_paths_result {
-    int64_t nf = 0, rows = 0, h2d = 0, d2h = 0;
-    HostBlock off, hops, rels, ncred, ntool;
+    int64_t nf = 0, rows = 0, n_links = 0, n_trows = 0, h2d = 0, d2h = 0;
+    HostBlock off, link_off, link_vs, link_rel, link_roff, link_toff, t_row, t_rel, findings;
+    std::mutex mu;
+    bool expanded = false;
+    HostBlock hops, rels, ncred, ntool;
 };
 extern "C" void abb_paths_result_free(abb_paths_result *r) {
     if (!r) return;
-    for (HostBlock *b : {&r->off, &r->hops, &r->rels, &r->ncred, &r->ntool}) b->release();
+    for (HostBlock *b : {&r->off, &r->link_off, &r->link_vs, &r->link_rel, &r->link_roff, &r->link_toff, &r->t_row, &r->t_rel, &r->findings, &r->hops, &r->rels,
+                         &r->ncred, &r->ntool})
+        b->release();
     delete r;
+}
+
+// links x templates -> flat rows (same layout the device's replicate kernel writes), threads over link ranges
+static bool paths_expand(abb_paths_result *r) {
+    std::lock_guard<std::mutex> lk(r->mu);
+    if (r->expanded) return true;
+    const size_t rows = static_cast<size_t>(r->rows);
+    if (!(r->hops.alloc(rows * 16) && r->rels.alloc(rows * 4) && r->ncred.alloc(rows * 4) && r->ntool.alloc(rows * 4))) return false;
+    const int64_t *loff = r->link_off.as<int64_t>(), *lroff = r->link_roff.as<int64_t>(), *ltoff = r->link_toff.as<int64_t>();
+    const int32_t *lvs = r->link_vs.as<int32_t>(), *fnd = r->findings.as<int32_t>(), *trow = r->t_row.as<int32_t>();
+    const int8_t *lrel = r->link_rel.as<int8_t>(), *trel = r->t_rel.as<int8_t>();
+    int32_t *hops = r->hops.as<int32_t>(), *ncred = r->ncred.as<int32_t>(), *ntool = r->ntool.as<int32_t>();
+    int8_t *rels = r->rels.as<int8_t>();
+    auto work = [&](int64_t f0, int64_t f1) {
+        for (int64_t fi = f0; fi < f1; fi++) {
+            const int32_t f = fnd[fi];
+            for (int64_t l = loff[fi]; l < loff[fi + 1]; l++) {
+                const int32_t vs = lvs[l]; const int8_t rvf = lrel[l];
+                const int64_t o0 = lroff[l], n = lroff[l + 1] - o0, t0 = ltoff[l];
+                for (int64_t k = 0; k < n; k++) {
+                    const int32_t *tr = trow + (t0 + k) * 4;
+                    const int32_t srv = tr[1];
+                    int32_t *h = hops + (o0 + k) * 4;
+                    h[0] = tr[0]; h[1] = srv; h[2] = (vs != srv) ? vs : -1; h[3] = f;
+                    int8_t *rr = rels + (o0 + k) * 4;
+                    const int8_t ras = trel[(t0 + k) * 2], rsv = trel[(t0 + k) * 2 + 1];
+                    if (vs != srv) { rr[0] = ras; rr[1] = rsv; rr[2] = rvf; rr[3] = -2; } else { rr[0] = ras; rr[1] = rvf; rr[2] = -2; rr[3] = -2; }
+                    ncred[o0 + k] = tr[2]; ntool[o0 + k] = tr[3];
+                }
+            }
+        }
+    };
+    const int nthreads = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(16, r->rows / (1 << 20))));
+    if (nthreads <= 1) work(0, r->nf);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nthreads; t++) th.emplace_back(work, r->nf * t / nthreads, r->nf * (t + 1) / nthreads);
+        for (auto &x : th) x.join();
+    }
+    r->expanded = true;
+    return true;
 }
 extern "C" int64_t abb_paths_result_rows(const abb_paths_result *r) { return r->rows; }
 extern "C" const int64_t *abb_paths_result_off(const abb_paths_result *r) { return r->off.as<int64_t>(); }
-extern "C" const int32_t *abb_paths_result_hops(const abb_paths_result *r) { return r->hops.as<int32_t>(); }
-extern "C" const int8_t *abb_paths_result_rels(const abb_paths_result *r) { return r->rels.as<int8_t>(); }
-extern "C" const int32_t *abb_paths_result_ncred(const abb_paths_result *r) { return r->ncred.as<int32_t>(); }
-extern "C" const int32_t *abb_paths_result_ntool(const abb_paths_result *r) { return r->ntool.as<int32_t>(); }
+extern "C" const int32_t *abb_paths_result_hops(const abb_paths_result *r) { return paths_expand(const_cast<abb_paths_result *>(r)) ? r->hops.as<int32_t>() : nullptr; }
+extern "C" const int8_t *abb_paths_result_rels(const abb_paths_result *r) { return paths_expand(const_cast<abb_paths_result *>(r)) ? r->rels.as<int8_t>() : nullptr; }
+extern "C" const int32_t *abb_paths_result_ncred(const abb_paths_result *r) { return paths_expand(const_cast<abb_paths_result *>(r)) ? r->ncred.as<int32_t>() : nullptr; }
+extern "C" const int32_t *abb_paths_result_ntool(const abb_paths_result *r) { return paths_expand(const_cast<abb_paths_result *>(r)) ? r->ntool.as<int32_t>() : nullptr; }
+extern "C" int64_t abb_paths_result_links(const abb_paths_result *r) { return r->n_links; }
+extern "C" int64_t abb_paths_result_template_rows(const abb_paths_result *r) { return r->n_trows; }
+extern "C" const int64_t *abb_paths_result_link_off(const abb_paths_result *r) { return r->link_off.as<int64_t>(); }
+extern "C" const int32_t *abb_paths_result_link_source(const abb_paths_result *r) { return r->link_vs.as<int32_t>(); }
+extern "C" const int8_t *abb_paths_result_link_rel(const abb_paths_result *r) { return r->link_rel.as<int8_t>(); }
+extern "C" const int64_t *abb_paths_result_link_row_off(const abb_paths_result *r) { return r->link_roff.as<int64_t>(); }
+extern "C" const int64_t *abb_paths_result_link_template(const abb_paths_result *r) { return r->link_toff.as<int64_t>(); }
+extern "C" const int32_t *abb_paths_result_template(const abb_paths_result *r) { return r->t_row.as<int32_t>(); }
+extern "C" const int8_t *abb_paths_result_template_rel(const abb_paths_result *r) { return r->t_rel.as<int8_t>(); }
 extern "C" int64_t abb_paths_result_h2d_bytes(const abb_paths_result *r) { return r->h2d; }
 extern "C" int64_t abb_paths_result_d2h_bytes(const abb_paths_result *r) { return r->d2h; }
 
@@ -880,41 +941,36 @@ static int paths_run(abb_graph *g, const int32_t *h_findings, const int32_t *d_f
     cudaStream_t st = g->stream;
     abb_paths_result *r = new abb_paths_result();
     r->nf = nf;
+    if (!r->findings.alloc(static_cast<size_t>(nf + 1) * 4)) { abb_paths_result_free(r); return fail(ABB_ERR_NOMEM, "pinned host allocation failed"); }
+    if (nf) memcpy(r->findings.p, h_findings, static_cast<size_t>(nf) * 4);
     if (!d_findings) {
-        if (int rc = g->p_findings.ensure(static_cast<size_t>(nf + 1) * 4)) { delete r; return rc; }
+        if (int rc = g->p_findings.ensure(static_cast<size_t>(nf + 1) * 4)) { abb_paths_result_free(r); return rc; }
         if (nf) { CUDA_TRY(cudaMemcpyAsync(g->p_findings.p, h_findings, static_cast<size_t>(nf) * 4, cudaMemcpyHostToDevice, st)); r->h2d += nf * 4; }
         d_findings = g->p_findings.as<int32_t>();
     }
-    if (int rc = g->p_off.ensure(static_cast<size_t>(nf + 1) * 8)) { delete r; return rc; }
+    if (int rc = g->p_off.ensure(static_cast<size_t>(nf + 1) * 8)) { abb_paths_result_free(r); return rc; }
     abb_paths_io io{};
     io.n_findings = nf; io.findings = d_findings; io.f_off = g->p_off.as<int64_t>();
     CUDA_TRY(cudaEventRecord(g->ev[2], st));
-    if (int rc = enqueue_paths_count(g, &io, st)) { delete r; return rc; }
-    int64_t total = 0;
-    CUDA_TRY(cudaMemcpyAsync(&total, io.f_off + nf, 8, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    r->rows = total;
-    const size_t rows = static_cast<size_t>(total);
-    int rc = g->p_hops.ensure(rows * 16 + 16);
-    if (!rc) rc = g->p_rels.ensure(rows * 4 + 16);
-    if (!rc) rc = g->p_ncred.ensure(rows * 4 + 16);
-    if (!rc) rc = g->p_ntool.ensure(rows * 4 + 16);
-    if (rc) { delete r; return rc; }
-    io.hops = g->p_hops.as<int32_t>(); io.rels = g->p_rels.as<int8_t>(); io.ncred = g->p_ncred.as<int32_t>(); io.ntool = g->p_ntool.as<int32_t>(); io.row_cap = total;
-    rc = enqueue_paths_fill(g, &io, st);
-    if (rc) { delete r; return rc; }
+    if (int rc = enqueue_paths_count(g, &io, st)) { abb_paths_result_free(r); return rc; }
     CUDA_TRY(cudaEventRecord(g->ev[3], st));
     g->paths_timed = true;
-    bool ok = r->off.alloc(static_cast<size_t>(nf + 1) * 8) && r->hops.alloc(rows * 16) && r->rels.alloc(rows * 4) && r->ncred.alloc(rows * 4) && r->ntool.alloc(rows * 4);
+    const PathsArgs &A = g->paths_args;
+    const size_t NL = static_cast<size_t>(g->paths_n_links), TR = static_cast<size_t>(g->paths_n_template_rows), n1 = static_cast<size_t>(nf) + 1;
+    r->n_links = g->paths_n_links; r->n_trows = g->paths_n_template_rows;
+    bool ok = r->off.alloc(n1 * 8) && r->link_off.alloc(n1 * 8) && r->link_vs.alloc(NL * 4) && r->link_rel.alloc(NL) && r->link_roff.alloc((NL + 1) * 8) &&
+              r->link_toff.alloc(NL * 8) && r->t_row.alloc(TR * 16) && r->t_rel.alloc(TR * 2);
     if (!ok) { abb_paths_result_free(r); return fail(ABB_ERR_NOMEM, "pinned host allocation failed"); }
-    cudaError_t e = cudaMemcpyAsync(r->off.p, io.f_off, static_cast<size_t>(nf + 1) * 8, cudaMemcpyDeviceToHost, st);
-    if (rows && e == cudaSuccess) e = cudaMemcpyAsync(r->hops.p, io.hops, rows * 16, cudaMemcpyDeviceToHost, st);
-    if (rows && e == cudaSuccess) e = cudaMemcpyAsync(r->rels.p, io.rels, rows * 4, cudaMemcpyDeviceToHost, st);
-    if (rows && e == cudaSuccess) e = cudaMemcpyAsync(r->ncred.p, io.ncred, rows * 4, cudaMemcpyDeviceToHost, st);
-    if (rows && e == cudaSuccess) e = cudaMemcpyAsync(r->ntool.p, io.ntool, rows * 4, cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaSuccess;
+    auto d2h = [&](HostBlock &dst, const void *src, size_t bytes) {
+        if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(dst.p, src, bytes, cudaMemcpyDeviceToHost, st);
+        r->d2h += static_cast<int64_t>(bytes);
+    };
+    d2h(r->off, io.f_off, n1 * 8); d2h(r->link_off, A.link_off, n1 * 8); d2h(r->link_vs, A.link_vs, NL * 4); d2h(r->link_rel, A.link_rel, NL);
+    d2h(r->link_roff, A.link_roff, (NL + 1) * 8); d2h(r->link_toff, A.link_toff, NL * 8); d2h(r->t_row, A.t_row, TR * 16); d2h(r->t_rel, A.t_rel, TR * 2);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { abb_paths_result_free(r); return fail(ABB_ERR_CUDA, "paths D2H failed: %s", cudaGetErrorString(e)); }
-    r->d2h = static_cast<int64_t>((nf + 1) * 8 + rows * 28);
+    r->rows = r->off.as<int64_t>()[nf];
     *out = r;
     return ABB_OK;
 }
@@ -938,7 +994,7 @@ extern "C" int abb_exposure_host(abb_graph *g, const int32_t *findings, int64_t 
     abb_walk_result *wr = nullptr;
     if (int rc = walk_collect(g, &spec, io, totals, h2d, &wr, false)) return rc;
     abb_paths_result *pr = nullptr;
-    int rc = paths_run(g, nullptr, g->d_roots.as<int32_t>(), n_findings, &pr);
+    int rc = paths_run(g, findings, g->d_roots.as<int32_t>(), n_findings, &pr);
     if (rc) { cudaStreamSynchronize(g->stream); abb_walk_result_free(wr); return rc; }
     *impact_out = wr; *paths_out = pr;
     return ABB_OK;

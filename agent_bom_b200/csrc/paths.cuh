@@ -46,6 +46,7 @@ struct PathsArgs {
     int32_t *link_vs;           // [n_links]
     int8_t *link_rel;           // [n_links] relationship of the pair (vs, finding)
     int64_t *link_rows;         // [n_links+1] rows per link, scanned into link_roff
+    int64_t *link_toff;         // [n_links] template offset of the link's vulnerable source
     int64_t *link_roff;         // [n_links+1]
     const unsigned long long *n_links;   // device scalar
     // templates: the rows of one vulnerable source, shared by every finding attached to it
@@ -264,7 +265,7 @@ __global__ void __launch_bounds__(256) template_kernel(const PathsArgs A) {
 
 __global__ void link_rows_kernel(const PathsArgs A) {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i < static_cast<int64_t>(*A.n_links)) A.link_rows[i] = A.t_cnt_node[A.link_vs[i]];
+    if (i < static_cast<int64_t>(*A.n_links)) { const int32_t vs = A.link_vs[i]; A.link_rows[i] = A.t_cnt_node[vs]; A.link_toff[i] = A.t_off_node[vs]; }
 }
 
 __global__ void finding_offsets_kernel(const PathsArgs A) {

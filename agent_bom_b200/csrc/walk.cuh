@@ -202,6 +202,24 @@ __device__ __forceinline__ Cand fetch_cand(const GraphView &g, const Frontier32 
     return c;
 }
 
+// fast path for a frontier chunk that holds ONE node (the common case on tree-like inventories): no prefix scan, no search
+template <bool NEED_META, bool NEED_EID>
+__device__ __forceinline__ Cand fetch_single(const GraphView &g, uint32_t sF, uint32_t dF, uint32_t sR, uint32_t total, uint32_t ci) {
+    Cand c; c.active = ci < total; c.owner = 0; c.meta = ABB_META_TRAVERSABLE; c.eid = 0; c.nbr = 0;
+    if (c.active) {
+        if (ci < dF) {
+            const uint32_t p = sF + ci; c.nbr = __ldg(g.fnbr + p);
+            if (NEED_META) c.meta = __ldg(g.fmeta + p);
+            if (NEED_EID) c.eid = __ldg(g.feid + p);
+        } else {
+            const uint32_t p = sR + (ci - dF); c.nbr = __ldg(g.rnbr + p);
+            if (NEED_META) c.meta = __ldg(g.rmeta + p);
+            if (NEED_EID) c.eid = __ldg(g.reid + p);
+        }
+    }
+    return c;
+}
+
 __device__ __forceinline__ bool cand_passes(const abb_walk_spec &sp, const Cand &c) {
     return c.active && ((sp.rel_mask >> (c.meta & ABB_META_REL_MASK)) & 1u) &&
            (!(sp.flags & ABB_WALK_TRAVERSABLE_ONLY) || (c.meta & ABB_META_TRAVERSABLE));
@@ -214,7 +232,7 @@ __device__ __forceinline__ bool type_emitted(uint32_t emit_types, uint8_t t) {
 // ---------------------------------------------------------------- one query
 // Returns false when the query outgrew the store (caller re-queues it for the next tier).
 template <class Store, bool NEED_META, bool BUDGET>
-__device__ bool walk_one(const WalkArgs &A, Store &st, int64_t q, int lane) {
+__device__ bool walk_one(const WalkArgs &A, Store &st, int64_t q, int lane, uint32_t *hist_bins) {
     const GraphView &g = A.g;
     const abb_walk_spec &sp = A.spec;
     const abb_walk_io &io = A.io;
@@ -272,13 +290,23 @@ __device__ bool walk_one(const WalkArgs &A, Store &st, int64_t q, int lane) {
     while (lvl_begin < lvl_end && (sp.max_depth < 0 || depth < sp.max_depth) && !stop) {
         if (depth + 1 > st.max_level()) { st.clear(tail, lane); return false; }
         for (idx_t base = lvl_begin; base < lvl_end && !stop; base += 32) {
-            idx_t fi = base + lane;
-            bool fvalid = fi < lvl_end;
-            int32_t u = fvalid ? st.q_get(fi) : 0;
-            Frontier32 f = load_frontier(g, sp.direction, u, fvalid);
+            const bool single = (lvl_end - base) == 1;
+            Frontier32 f; f.sF = f.dF = f.sR = f.excl = f.total = 0;
+            if (single) {
+                const int32_t u = st.q_get(base);
+                uint32_t dR = 0;
+                if (sp.direction & 1) { const uint32_t a = __ldg(g.foff + u), b = __ldg(g.foff + u + 1); f.sF = a; f.dF = b - a; }
+                if (sp.direction & 2) { const uint32_t a = __ldg(g.roff + u), b = __ldg(g.roff + u + 1); f.sR = a; dR = b - a; }
+                f.total = f.dF + dR;
+            } else {
+                idx_t fi = base + lane;
+                bool fvalid = fi < lvl_end;
+                int32_t u = fvalid ? st.q_get(fi) : 0;
+                f = load_frontier(g, sp.direction, u, fvalid);
+            }
             exp_end = (base + 32 < lvl_end) ? base + 32 : lvl_end;
             for (uint32_t c0 = 0; c0 < f.total && !stop; c0 += 32) {
-                Cand c = fetch_cand<NEED_META, false>(g, f, c0 + lane);
+                Cand c = single ? fetch_single<NEED_META, false>(g, f.sF, f.dF, f.sR, f.total, c0 + lane) : fetch_cand<NEED_META, false>(g, f, c0 + lane);
                 bool pass = cand_passes(sp, c);
                 unsigned pm = __ballot_sync(FULL, pass);
                 if (BUDGET && sp.max_edges >= 0) {
@@ -347,7 +375,8 @@ __device__ bool walk_one(const WalkArgs &A, Store &st, int64_t q, int lane) {
     if (lane == 0) start = atomicAdd(io.totals, static_cast<unsigned long long>(count));
     start = __shfl_sync(FULL, start, 0);
     const bool fits = static_cast<long long>(start) + count <= io.node_cap;
-    uint32_t hist_acc = 0;
+    if ((fl & ABB_WALK_HIST) && lane < ABB_N_ENTITY_TYPES) hist_bins[lane] = 0;
+    __syncwarp();
     if (fits || (fl & ABB_WALK_HIST)) {
         unsigned long long w = start;
         for (idx_t i = first; i < tail; i += 32) {
@@ -367,16 +396,16 @@ __device__ bool walk_one(const WalkArgs &A, Store &st, int64_t q, int lane) {
             w += __popc(okm);
             if (fl & ABB_WALK_HIST) {
                 // roots are never counted (impact_of excludes the source, container.py:265)
-                bool hv = ok && (k >= n_roots || A.hist_roots) && t < ABB_N_ENTITY_TYPES;
-#pragma unroll
-                for (int b = 0; b < ABB_N_ENTITY_TYPES; b++) {
-                    unsigned bm = __ballot_sync(FULL, hv && t == b);
-                    if (lane == b) hist_acc += __popc(bm);
-                }
+                const bool hv = ok && (k >= n_roots || A.hist_roots) && t < ABB_N_ENTITY_TYPES;
+                // one lane per distinct type in the chunk adds the whole group's count to that type's bin
+                const unsigned tm = __match_any_sync(FULL, hv ? static_cast<int>(t) : (-1 - lane));
+                if (hv && (__ffs(tm) - 1) == lane) hist_bins[t] += __popc(tm);
+                __syncwarp();
             }
         }
     }
-    if ((fl & ABB_WALK_HIST) && lane < ABB_N_ENTITY_TYPES) io.q_hist[q * ABB_N_ENTITY_TYPES + lane] = hist_acc;
+    __syncwarp();
+    if ((fl & ABB_WALK_HIST) && lane < ABB_N_ENTITY_TYPES) io.q_hist[q * ABB_N_ENTITY_TYPES + lane] = hist_bins[lane];
 
     // ---- recorded edges: re-scan the expanded prefix in the same order (container.py:512-513)
     unsigned long long estart = 0;
@@ -431,6 +460,7 @@ __device__ __forceinline__ int64_t next_chunk(unsigned long long *ctl, int lane)
 template <int H, int Q, bool PAR, bool NEED_META, bool BUDGET, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) walk_smem_kernel(const WalkArgs A) {
     extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ uint32_t s_hist[WARPS][ABB_N_ENTITY_TYPES];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     using Store = SmemStore<H, Q, PAR>;
     constexpr int kStride = (Store::kBytes + 15) & ~15;
@@ -444,7 +474,7 @@ __global__ void __launch_bounds__(WARPS * 32) walk_smem_kernel(const WalkArgs A)
         int64_t ce = c + WORK_CHUNK < nq ? c + WORK_CHUNK : nq;
         for (int64_t i = c; i < ce; i++) {
             int64_t q = A.qlist ? A.qlist[i] : i;
-            if (!walk_one<Store, NEED_META, BUDGET>(A, st, q, lane)) {
+            if (!walk_one<Store, NEED_META, BUDGET>(A, st, q, lane, s_hist[warp])) {
                 if (lane == 0) { unsigned long long k = atomicAdd(A.ctl + 1, 1ull); A.overflow[k] = static_cast<int32_t>(q); }
             }
         }
@@ -453,6 +483,7 @@ __global__ void __launch_bounds__(WARPS * 32) walk_smem_kernel(const WalkArgs A)
 
 template <bool NEED_META, bool BUDGET>
 __global__ void __launch_bounds__(128) walk_global_kernel(const WalkArgs A) {
+    __shared__ uint32_t s_hist[4][ABB_N_ENTITY_TYPES];
     const int lane = threadIdx.x & 31;
     const int64_t slot = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     GlobalStore st;
@@ -468,7 +499,7 @@ __global__ void __launch_bounds__(128) walk_global_kernel(const WalkArgs A) {
         int64_t i = static_cast<int64_t>(__shfl_sync(FULL, v, 0));
         if (i >= nq) break;
         int64_t q = A.qlist ? A.qlist[i] : i;
-        if (!walk_one<GlobalStore, NEED_META, BUDGET>(A, st, q, lane)) {
+        if (!walk_one<GlobalStore, NEED_META, BUDGET>(A, st, q, lane, s_hist[threadIdx.x >> 5])) {
             if (lane == 0) atomicExch(A.ctl + 2, 1ull);  // cannot happen unless scratch is undersized
         }
     }

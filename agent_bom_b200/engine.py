@@ -85,6 +85,15 @@ class PathRows:
     h2d_bytes: int = 0
     d2h_bytes: int = 0
     kernel_ms: float = 0.0
+    # factorised form (what actually crossed PCIe): rows of finding i = for each link l in [link_off[i], link_off[i+1]):
+    # the template rows [link_template[l], +link_row_off[l+1]-link_row_off[l]) of vulnerable source link_source[l]
+    link_off: np.ndarray | None = None
+    link_source: np.ndarray | None = None
+    link_rel: np.ndarray | None = None
+    link_row_off: np.ndarray | None = None
+    link_template: np.ndarray | None = None
+    template: np.ndarray | None = None       # int32 [T,4] agent, server, ncred, ntool
+    template_rel: np.ndarray | None = None   # int8 [T,2]
 
 
 class DeviceGraph:
@@ -242,6 +251,13 @@ class DeviceGraph:
             rels=np.ascontiguousarray(_view(lib.abb_paths_result_rels(res), rows * 4, np.int8).reshape(rows, 4)[:, :3]), ncred=_view(lib.abb_paths_result_ncred(res), rows, np.int32),
             ntool=_view(lib.abb_paths_result_ntool(res), rows, np.int32),
             h2d_bytes=int(lib.abb_paths_result_h2d_bytes(res)), d2h_bytes=int(lib.abb_paths_result_d2h_bytes(res)),
+            link_off=_view(lib.abb_paths_result_link_off(res), nf + 1, np.int64),
+            link_source=_view(lib.abb_paths_result_link_source(res), int(lib.abb_paths_result_links(res)), np.int32),
+            link_rel=_view(lib.abb_paths_result_link_rel(res), int(lib.abb_paths_result_links(res)), np.int8),
+            link_row_off=_view(lib.abb_paths_result_link_row_off(res), int(lib.abb_paths_result_links(res)) + 1, np.int64),
+            link_template=_view(lib.abb_paths_result_link_template(res), int(lib.abb_paths_result_links(res)), np.int64),
+            template=_view(lib.abb_paths_result_template(res), int(lib.abb_paths_result_template_rows(res)) * 4, np.int32).reshape(-1, 4),
+            template_rel=_view(lib.abb_paths_result_template_rel(res), int(lib.abb_paths_result_template_rows(res)) * 2, np.int8).reshape(-1, 2),
         )
 
     def exposure_paths_many(self, findings) -> PathRows:

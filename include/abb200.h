@@ -254,8 +254,20 @@ int abb_paths_count_launch(abb_graph *g, const abb_paths_io *io, void *stream);
 /* pass 2: fill rows (requires row_cap >= total) */
 int abb_paths_fill_launch(abb_graph *g, const abb_paths_io *io, void *stream);
 
+/* Host-buffer form.  What crosses PCIe is the factorised result — per finding its links (vulnerable source +
+ * relationship of the pair (source, finding)), per link the template slice of that source — which determines every
+ * row; the flat hops/rels/ncred/ntool arrays are expanded from it on the host the first time they are asked for. */
 typedef struct abb_paths_result abb_paths_result;
 int abb_paths_host(abb_graph *g, const int32_t *findings, int64_t n_findings, abb_paths_result **out);
+int64_t abb_paths_result_links(const abb_paths_result *r);
+int64_t abb_paths_result_template_rows(const abb_paths_result *r);
+const int64_t *abb_paths_result_link_off(const abb_paths_result *r);      /* [n_findings+1] links of finding i */
+const int32_t *abb_paths_result_link_source(const abb_paths_result *r);   /* [n_links] vulnerable source */
+const int8_t *abb_paths_result_link_rel(const abb_paths_result *r);       /* [n_links] relationship (source, finding) */
+const int64_t *abb_paths_result_link_row_off(const abb_paths_result *r);  /* [n_links+1] first flat row of each link */
+const int64_t *abb_paths_result_link_template(const abb_paths_result *r); /* [n_links] first template row of the link's source */
+const int32_t *abb_paths_result_template(const abb_paths_result *r);      /* [n_template_rows*4] agent, server, ncred, ntool */
+const int8_t *abb_paths_result_template_rel(const abb_paths_result *r);   /* [n_template_rows*2] (agent,server), (server,source) */
 int64_t abb_paths_result_rows(const abb_paths_result *r);
 const int64_t *abb_paths_result_off(const abb_paths_result *r); /* [n_findings+1] */
 const int32_t *abb_paths_result_hops(const abb_paths_result *r);

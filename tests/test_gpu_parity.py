@@ -212,6 +212,20 @@ def test_exposure_path_rows(key):
     np.testing.assert_array_equal(got.ncred, want.ncred)
     np.testing.assert_array_equal(got.ntool, want.ntool)
     assert int(got.off[-1]) == want.hops.shape[0]
+    # the factorised form that crossed PCIe expands to the same rows
+    nf = len(f)
+    k = 0
+    for i in range(nf):
+        for l in range(int(got.link_off[i]), int(got.link_off[i + 1])):
+            n = int(got.link_row_off[l + 1] - got.link_row_off[l])
+            t0 = int(got.link_template[l])
+            assert int(got.link_row_off[l]) == k
+            np.testing.assert_array_equal(got.template[t0: t0 + n, 0], got.hops[k: k + n, 0])
+            np.testing.assert_array_equal(got.template[t0: t0 + n, 2], got.ncred[k: k + n])
+            assert (got.hops[k: k + n, 3] == f[i]).all()
+            k += n
+        if i > 200:
+            break
 
 
 @pytest.mark.parametrize("name", ALL_FIXTURES)
