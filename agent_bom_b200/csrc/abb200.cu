@@ -183,6 +183,7 @@ struct abb_graph {
     DevBuf dd_sig, dd_ssig, dd_q, dd_sq, dd_head, dd_gid, dd_hp, dd_glen, dd_goff, dd_arena, dd_memoff, dd_memsrc, dd_memstate, dd_indiv, dd_cnt, dd_tmp;
     DevBuf dd_gstart, dd_gcount, dd_gmaxd, dd_gflags, dd_ghist;
     bool dedup_enabled = true;
+    int s1_cfg = 0;   // 0: 1024-slot hash / 512-entry queue, 1: 512/256 (more resident warps, earlier overflow)
     DevBuf identity_rank;
     // host-API staging
     DevBuf d_roots, d_root_off, d_targets, d_qstart, d_qcount, d_qmaxd, d_qflags, d_qestart, d_qecount, d_qhist;
@@ -218,10 +219,10 @@ static int graph_finish_init(abb_graph *g) {
     if (int rc = g->ctl.ensure(64 * sizeof(unsigned long long))) return rc;
     const int64_t n = g->v.n;
     g->g_words = (n + 31) / 32 + 1;
-    // tier G1: 24 warps per SM (latency-bound pointer chasing wants every warp it can get), queue bounded at 64K entries
+    // tier G1: 40 warps per SM (latency-bound pointer chasing wants every warp it can get), queue bounded at 64K entries
     g->g_qcap = std::min<int64_t>(n + 4096, 1 << 16);
-    g->g_slots = g->sm_count * 24;
-    if (const char *e = getenv("ABB_G1_WARPS_PER_SM")) g->g_slots = g->sm_count * std::max(4, std::min(32, atoi(e)));
+    g->g_slots = g->sm_count * 40;
+    if (const char *e = getenv("ABB_G1_WARPS_PER_SM")) g->g_slots = g->sm_count * std::max(4, std::min(40, atoi(e)));
     {
         const size_t sl = static_cast<size_t>(g->g_slots);
         if (int rc = g->g_bitmap.ensure(sl * g->g_words * 4)) return rc;
@@ -242,6 +243,7 @@ static int graph_finish_init(abb_graph *g) {
         CUDA_TRY(cudaMemset(g->x_bitmap.p, 0, sl * g->g_words * 4));
     }
     if (const char *e = getenv("ABB_DEDUP")) g->dedup_enabled = atoi(e) != 0;
+    if (const char *e = getenv("ABB_S1_CFG")) g->s1_cfg = atoi(e);
     if (!g->v.rank) {
         if (int rc = g->identity_rank.ensure(static_cast<size_t>(n + 1) * 4)) return rc;
         std::vector<int32_t> id(static_cast<size_t>(n));
@@ -455,7 +457,8 @@ static int enqueue_tiers(abb_graph *g, WalkArgs A, int64_t max_items, unsigned l
     const bool meta = A.spec.rel_mask != 0xFFFFFFFFu || (fl & ABB_WALK_TRAVERSABLE_ONLY);
     const bool bud = A.spec.max_nodes >= 0 || A.spec.max_edges >= 0;
     A.ctl = ctl; A.overflow = ov1;
-    if (int rc = launch_smem_variant<S1_H, S1_Q, S1_WARPS>(g, A, max_items, par, meta, bud, st)) return rc;
+    if (g->s1_cfg == 1) { if (int rc = launch_smem_variant<512, 256, 8>(g, A, max_items, par, meta, bud, st)) return rc; }
+    else if (int rc = launch_smem_variant<S1_H, S1_Q, S1_WARPS>(g, A, max_items, par, meta, bud, st)) return rc;
     A.qlist = ov1; A.nq = 0; A.nq_dev = ctl + 1; A.ctl = ctl + 4; A.overflow = ov2;
     A.g_bitmap = g->g_bitmap.as<uint32_t>(); A.g_queue = g->g_queue.as<int32_t>(); A.g_par = g->g_par.as<int32_t>(); A.g_dep = g->g_dep.as<int32_t>();
     A.g_words = g->g_words; A.g_qcap = g->g_qcap;

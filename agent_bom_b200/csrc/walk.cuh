@@ -289,6 +289,22 @@ __device__ bool walk_one(const WalkArgs &A, Store &st, int64_t q, int lane, uint
 
     while (lvl_begin < lvl_end && (sp.max_depth < 0 || depth < sp.max_depth) && !stop) {
         if (depth + 1 > st.max_level()) { st.clear(tail, lane); return false; }
+        if (A.overflow != nullptr && lvl_end - lvl_begin > 1) {
+            // level forecast: if this level's candidates exceed several times the room left in this tier's queue the walk
+            // will almost surely outgrow it — move it to the next tier now rather than after filling the queue
+            unsigned long long cand = 0;
+            for (idx_t base = lvl_begin; base < lvl_end; base += 32) {
+                const idx_t fi = base + lane;
+                if (fi < lvl_end) {
+                    const int32_t u = st.q_get(fi);
+                    if (sp.direction & 1) cand += __ldg(g.foff + u + 1) - __ldg(g.foff + u);
+                    if (sp.direction & 2) cand += __ldg(g.roff + u + 1) - __ldg(g.roff + u);
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) cand += __shfl_xor_sync(FULL, cand, o);
+            if (cand > 3ull * static_cast<unsigned long long>(st.qcap() - tail) + 64ull) { st.clear(tail, lane); return false; }
+        }
         for (idx_t base = lvl_begin; base < lvl_end && !stop; base += 32) {
             const bool single = (lvl_end - base) == 1;
             Frontier32 f; f.sF = f.dF = f.sR = f.excl = f.total = 0;
@@ -305,8 +321,13 @@ __device__ bool walk_one(const WalkArgs &A, Store &st, int64_t q, int lane, uint
                 f = load_frontier(g, sp.direction, u, fvalid);
             }
             exp_end = (base + 32 < lvl_end) ? base + 32 : lvl_end;
+            // software pipeline: the next chunk's neighbour loads are in flight while this chunk's visited-set round trip resolves
+            Cand nxt;
+            if (f.total) nxt = single ? fetch_single<NEED_META, false>(g, f.sF, f.dF, f.sR, f.total, lane) : fetch_cand<NEED_META, false>(g, f, lane);
             for (uint32_t c0 = 0; c0 < f.total && !stop; c0 += 32) {
-                Cand c = single ? fetch_single<NEED_META, false>(g, f.sF, f.dF, f.sR, f.total, c0 + lane) : fetch_cand<NEED_META, false>(g, f, c0 + lane);
+                Cand c = nxt;
+                if (c0 + 32 < f.total)
+                    nxt = single ? fetch_single<NEED_META, false>(g, f.sF, f.dF, f.sR, f.total, c0 + 32 + lane) : fetch_cand<NEED_META, false>(g, f, c0 + 32 + lane);
                 bool pass = cand_passes(sp, c);
                 unsigned pm = __ballot_sync(FULL, pass);
                 if (BUDGET && sp.max_edges >= 0) {
@@ -482,7 +503,7 @@ __global__ void __launch_bounds__(WARPS * 32) walk_smem_kernel(const WalkArgs A)
 }
 
 template <bool NEED_META, bool BUDGET>
-__global__ void __launch_bounds__(128) walk_global_kernel(const WalkArgs A) {
+__global__ void __launch_bounds__(128, 10) walk_global_kernel(const WalkArgs A) {
     __shared__ uint32_t s_hist[4][ABB_N_ENTITY_TYPES];
     const int lane = threadIdx.x & 31;
     const int64_t slot = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -500,7 +521,10 @@ __global__ void __launch_bounds__(128) walk_global_kernel(const WalkArgs A) {
         if (i >= nq) break;
         int64_t q = A.qlist ? A.qlist[i] : i;
         if (!walk_one<GlobalStore, NEED_META, BUDGET>(A, st, q, lane, s_hist[threadIdx.x >> 5])) {
-            if (lane == 0) atomicExch(A.ctl + 2, 1ull);  // cannot happen unless scratch is undersized
+            if (lane == 0) {
+                if (A.overflow) { unsigned long long k = atomicAdd(A.ctl + 1, 1ull); A.overflow[k] = static_cast<int32_t>(q); }   // G1 -> GX
+                else atomicExch(A.ctl + 2, 1ull);   // GX: cannot happen unless the whole-graph scratch is undersized
+            }
         }
     }
 }

@@ -302,3 +302,24 @@ def test_empty_and_ragged_batches():
     spec = dg.spec_traverse(3, 4, -1, -1, False, 0, False, False, True)
     got = dg.walk(spec, np.asarray([1, 2], dtype=np.int32), np.asarray([0, 0, 2], dtype=np.int64))
     assert int(got.count[0]) == 0 and int(got.flags[0]) & 2
+
+
+def test_whole_graph_walks_reach_the_last_tier():
+    """Unbounded walks over a dense seeded graph outgrow the shared-memory and bounded-queue tiers (S1 -> G1 -> GX)."""
+    og, dg, _, _, _ = graphs_for((30000, 400000, 4))
+    rng = np.random.default_rng(29)
+    sources = rng.integers(0, og.n_nodes, size=12).astype(np.int32)
+    want = orc.distances_many(og, sources, 0xFFFFFFFF)
+    assert int(np.diff(want.off).max()) > 20000          # really whole-graph
+    for dedup in (True, False):
+        dg.set_dedup(dedup)
+        got = dg.walk(dg.spec_distances(0xFFFFFFFF), sources)
+        assert_slices_equal(got, want, gpu_aux="depth")
+    dg.set_dedup(True)
+    spec = dg.spec_traverse(3, 12, -1, -1, False, 0, False, False, True)
+    roots = sources[:4]
+    root_off = np.arange(5, dtype=np.int64)
+    want_t = orc.traverse_many(og, roots, root_off, direction=3, max_depth=12)
+    got_t = dg.walk(spec, roots, root_off)
+    assert_slices_equal(got_t, want_t, gpu_aux="depth")
+    np.testing.assert_array_equal(got_t.ecount, np.diff(want_t.eoff))
