@@ -84,6 +84,7 @@ EXPORTS = {
     "abb_spec_traverse_subgraph": (WalkSpec, [i32, i32, i64, i64, i32, u32, i32, i32, i32]),
     "abb_spec_distances_along": (WalkSpec, [u32, u32]),
     "abb_walk_launch": (C.c_int, [vp, C.POINTER(WalkSpec), C.POINTER(WalkIO), vp]),
+    "abb_walk_signatures": (C.c_int, [vp, C.POINTER(WalkSpec), vp, i64, vp, vp]),
     "abb_launch_count": (i64, []),
     "abb_last_walk_ms": (C.c_float, [vp]),
     "abb_last_paths_ms": (C.c_float, [vp]),

@@ -589,6 +589,16 @@ extern "C" int abb_walk_launch(abb_graph *g, const abb_walk_spec *spec, const ab
     return ABB_OK;
 }
 
+extern "C" int abb_walk_signatures(abb_graph *g, const abb_walk_spec *spec, const int32_t *roots, int64_t n, unsigned long long *sig, void *stream) {
+    if (!g || !spec || n < 0 || (n && (!roots || !sig))) return fail(ABB_ERR_ARG, "bad arguments");
+    if (!n) return ABB_OK;
+    DeviceGuard dg(g->device);
+    dedup_sig_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(g->v, *spec, roots, n, sig, nullptr);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return ABB_OK;
+}
+
 extern "C" float abb_last_walk_ms(abb_graph *g) {
     if (!g || !g->walk_timed) return -1.f;
     DeviceGuard dg(g->device);

@@ -71,7 +71,8 @@ __global__ void dedup_sig_kernel(GraphView g, abb_walk_spec sp, const int32_t *r
         for (int i = 0; i < n; i++) h = mix64(h ^ (static_cast<unsigned long long>(static_cast<uint32_t>(lst[i])) + (static_cast<unsigned long long>(i + 1) << 32)));
         h &= ~SIG_INELIGIBLE;
     }
-    sig[q] = h; qidx[q] = static_cast<int32_t>(q);
+    sig[q] = h;
+    if (qidx) qidx[q] = static_cast<int32_t>(q);
 }
 
 // per sorted position: group-head flag; ineligible sources go straight to the individual list.

@@ -26,6 +26,19 @@ def _stream_ptr(stream: torch.cuda.Stream | None):
     return C.c_void_p(s.cuda_stream)
 
 
+def frontier_signatures(dg: DeviceGraph, spec, roots: torch.Tensor, stream: torch.cuda.Stream | None = None) -> torch.Tensor:
+    """int64 signature of every source's depth-1 frontier (negative = walked individually); equal signatures share a traversal."""
+    assert roots.dtype == torch.int32 and roots.is_cuda
+    sig = torch.empty(roots.shape[0], dtype=torch.int64, device=roots.device)
+    _lib.check(_lib.load().abb_walk_signatures(dg.handle, C.byref(spec), _ptr(roots), int(roots.shape[0]), _ptr(sig), _stream_ptr(stream)))
+    return sig
+
+
+def shard_by_signature(sig: torch.Tensor, world: int, rank: int) -> torch.Tensor:
+    """Boolean mask of the sources this rank owns: all sources of one frontier group land on the same rank."""
+    return ((sig & 0x7FFFFFFFFFFFFFFF) % world) == rank
+
+
 class DeviceWalk:
     """Reusable output buffers + launch for one walk spec over batches of up to ``max_queries`` queries."""
 

@@ -210,8 +210,10 @@ def main() -> int:
 
     from agent_bom_b200 import _lib, dist as abdist
     from agent_bom_b200.engine import DeviceGraph
-    from agent_bom_b200.torch_api import DevicePaths, DeviceWalk
+    from agent_bom_b200.torch_api import DevicePaths, DeviceWalk, frontier_signatures, shard_by_signature
 
+    # keep stdout to the single JSON line: NCCL's version banner / debug output goes to a file
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/abb200_nccl.%h.%p.log")
     info = abdist.init_from_env("nccl" if int(os.environ.get("WORLD_SIZE", "1")) > 1 else None)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback (use --impl reference for the CPU port)")
@@ -230,8 +232,14 @@ def main() -> int:
     torch.cuda.synchronize()
     t_bcast = time.perf_counter() - t0
     dg = DeviceGraph.adopt(tensors, n_nodes, n_entries, info.local_rank)
-    lo, hi = abdist.shard_bounds(findings_all.shape[0], info.world, info.rank)
-    my = findings_all[lo:hi].contiguous()
+    # shard by depth-1 frontier signature: every finding of one frontier group lands on the same rank, so the
+    # de-duplicated traversal of that group runs once in the whole job (a positional split would repeat it per rank)
+    spec = DeviceGraph.spec_impact_of(MAX_DEPTH)
+    if info.world > 1:
+        sig = frontier_signatures(dg, spec, findings_all)
+        my = findings_all[shard_by_signature(sig, info.world, info.rank)].contiguous()
+    else:
+        my = findings_all
     my_host = my.cpu().numpy()
     nq = int(my.shape[0])
     batch = max(1, min(args.batch, nq))
@@ -239,7 +247,6 @@ def main() -> int:
     log(f"[bench] rank {info.rank}/{info.world}: {nq:,} findings in {len(batches)} batches of <= {batch:,}; CSR replicate {t_bcast:.2f}s ({dg.nbytes / 1e9:.2f} GB)")
 
     # ---- device-resident leg: buffers sized by a first fitted pass
-    spec = DeviceGraph.spec_impact_of(MAX_DEPTH)
     walk = DeviceWalk(dg, spec, batch, node_cap=1 << 20)
     paths = DevicePaths(dg, batch)
     need_nodes = need_rows = 0
@@ -287,6 +294,8 @@ def main() -> int:
             paths.count(my[s:e])
             paths.fill(my[s:e])
 
+    clocks = ClockSampler(info.local_rank)
+    clocks.__enter__()                       # sampled from the warm-up through the end of the e2e leg (all under load)
     for _ in range(args.warmup):
         one_step()
     torch.cuda.synchronize()
@@ -294,13 +303,12 @@ def main() -> int:
     launches0 = lib.abb_launch_count()
     walk_events: list = []
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(info.local_rank) as clocks:
-        torch.cuda.synchronize()
-        start.record()
-        for _ in range(args.steps):
-            one_step(walk_events)
-        end.record()
-        torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    start.record()
+    for _ in range(args.steps):
+        one_step(walk_events)
+    end.record()
+    torch.cuda.synchronize()
     abdist.barrier(info)
     launches = lib.abb_launch_count() - launches0
     dev_ms = start.elapsed_time(end)
@@ -327,6 +335,7 @@ def main() -> int:
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     abdist.barrier(info)
+    clocks.__exit__(None, None, None)
     e2e_s_max = abdist.max_over_ranks(e2e_s, info, device)
     e2e_value = total_findings * args.steps / e2e_s_max
     h2d_all = abdist.sum_over_ranks(h2d, info, device)
@@ -352,7 +361,7 @@ def main() -> int:
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": info.world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {
-                "workload": f"{desc}, all finding nodes as sources, sharded across {info.world} GPU(s)", "nodes": n_nodes, "adjacency_entries_per_direction": n_entries,
+                "workload": f"{desc}, all finding nodes as sources, sharded across {info.world} GPU(s) by frontier signature", "nodes": n_nodes, "adjacency_entries_per_direction": n_entries,
                 "findings": total_findings, "max_depth": MAX_DEPTH, "batch": batch, "seed": args.seed,
                 "estate_knobs": "creds_per_server=20, cred_bucket=80, vulns_per_server=8 (agent_bom_b200.estate.BENCH_KNOBS)",
                 "l2": "inputs larger than L2 (CSR >> 126 MB; no flush)" if dg.nbytes > 400e6 else "CSR smaller than L2; no flush (reported as is)",
@@ -366,6 +375,10 @@ def main() -> int:
         }
         print(json.dumps(line), flush=True)
     abdist.barrier(info)
+    if info.world > 1:
+        import torch.distributed as tdist
+
+        tdist.destroy_process_group()
     return 0
 
 

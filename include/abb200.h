@@ -194,6 +194,10 @@ typedef struct abb_walk_io {
 
 /* Enqueue the walk on `stream` (a cudaStream_t, NULL = default stream).  Asynchronous. */
 int abb_walk_launch(abb_graph *g, const abb_walk_spec *spec, const abb_walk_io *io, void *stream);
+/* 64-bit signature of each single-source query's depth-1 frontier (device arrays).  Sources with equal signatures
+ * share one traversal when walked in the same batch, so multi-GPU runs shard the source list by signature
+ * (sig mod world) instead of by position; bit 63 marks sources that are walked individually. */
+int abb_walk_signatures(abb_graph *g, const abb_walk_spec *spec, const int32_t *roots, int64_t n, unsigned long long *sig, void *stream);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 int64_t abb_launch_count(void);
 /* Timing hooks: elapsed milliseconds of the walk kernels of the most recent
