@@ -87,6 +87,7 @@ EXPORTS = {
     "abb_walk_signatures": (C.c_int, [vp, C.POINTER(WalkSpec), vp, i64, vp, vp]),
     "abb_launch_count": (i64, []),
     "abb_last_walk_ms": (C.c_float, [vp]),
+    "abb_last_walk_stats": (C.c_int, [vp, vp]),
     "abb_last_paths_ms": (C.c_float, [vp]),
     "abb_walk_host": (C.c_int, [vp, C.POINTER(WalkSpec), vp, vp, vp, i64, C.POINTER(vp)]),
     "abb_walk_result_queries": (i64, [vp]),

@@ -183,6 +183,8 @@ struct abb_graph {
     DevBuf dd_sig, dd_ssig, dd_q, dd_sq, dd_head, dd_gid, dd_hp, dd_glen, dd_goff, dd_arena, dd_memoff, dd_memsrc, dd_memstate, dd_indiv, dd_cnt, dd_tmp;
     DevBuf dd_gstart, dd_gcount, dd_gmaxd, dd_gflags, dd_ghist;
     bool dedup_enabled = true;
+    int64_t last_walk_queries = 0;
+    bool last_walk_dedup = false;
     int s1_cfg = 0;   // 0: 1024-slot hash / 512-entry queue, 1: 512/256 (more resident warps, earlier overflow)
     DevBuf identity_rank;
     // host-API staging
@@ -569,7 +571,9 @@ static int enqueue_walk(abb_graph *g, const abb_walk_spec *spec, const abb_walk_
     if (int rc = g->ov1.ensure(static_cast<size_t>(io->n_queries) * 4)) return rc;
     if (int rc = g->ov2.ensure(static_cast<size_t>(io->n_queries) * 4)) return rc;
     CUDA_TRY(cudaMemsetAsync(g->ctl.p, 0, 64 * sizeof(unsigned long long), st));
-    if (dedup_applies(g, spec, io)) return enqueue_dedup_walk(g, spec, io, st);
+    g->last_walk_queries = io->n_queries;
+    g->last_walk_dedup = dedup_applies(g, spec, io);
+    if (g->last_walk_dedup) return enqueue_dedup_walk(g, spec, io, st);
     WalkArgs A{};
     A.g = g->v; A.spec = *spec; A.io = *io;
     A.qlist = nullptr; A.nq = io->n_queries; A.nq_dev = nullptr;
@@ -607,6 +611,19 @@ extern "C" float abb_last_walk_ms(abb_graph *g) {
     if (cudaEventElapsedTime(&ms, g->ev[0], g->ev[1]) != cudaSuccess) return -1.f;
     return ms;
 }
+extern "C" int abb_last_walk_stats(abb_graph *g, int64_t *out4) {
+    if (!g || !out4) return fail(ABB_ERR_ARG, "null argument");
+    DeviceGuard dg(g->device);
+    std::lock_guard<std::mutex> lk(g->mu);
+    out4[0] = g->last_walk_queries; out4[1] = out4[2] = out4[3] = 0;
+    if (g->last_walk_dedup && g->dd_cnt.p) {
+        unsigned long long c[3] = {0, 0, 0};
+        CUDA_TRY(cudaMemcpy(c, g->dd_cnt.p, sizeof c, cudaMemcpyDeviceToHost));
+        out4[1] = static_cast<int64_t>(c[0]); out4[2] = static_cast<int64_t>(c[1]); out4[3] = static_cast<int64_t>(c[2]);
+    }
+    return ABB_OK;
+}
+
 extern "C" float abb_last_paths_ms(abb_graph *g) {
     if (!g || !g->paths_timed) return -1.f;
     DeviceGuard dg(g->device);

@@ -318,5 +318,11 @@ class DeviceGraph:
     def last_walk_ms(self) -> float:
         return float(_lib.load().abb_last_walk_ms(self.handle))
 
+    def last_walk_stats(self) -> dict:
+        """Sharing statistics of the most recent walk: how many sources collapsed into how many traversals."""
+        out = (C.c_int64 * 4)()
+        _lib.check(_lib.load().abb_last_walk_stats(self.handle, out))
+        return {"queries": int(out[0]), "groups": int(out[1]), "individual": int(out[2]), "eligible": int(out[3])}
+
     def last_paths_ms(self) -> float:
         return float(_lib.load().abb_last_paths_ms(self.handle))

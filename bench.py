@@ -310,6 +310,7 @@ def main() -> int:
     end.record()
     torch.cuda.synchronize()
     abdist.barrier(info)
+    walk_stats = dg.last_walk_stats()
     launches = lib.abb_launch_count() - launches0
     dev_ms = start.elapsed_time(end)
     walk_ms = sum(a.elapsed_time(b) for a, b in walk_events)
@@ -354,9 +355,24 @@ def main() -> int:
             algo_bytes_per_step = bytes_per * nq
             walk_ms_per_step = walk_ms / args.steps
             achieved = algo_bytes_per_step / (walk_ms_per_step / 1000.0) / 1e9
-            roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                        "kernel": "walk_smem_kernel (+ overflow tiers) of abb_walk_launch", "algorithmic_bytes_per_traversal": bytes_per,
-                        "bytes_estimated_from": f"oracle counters on {len(sample):,} sampled findings", "walk_ms_per_step": walk_ms_per_step, "peak_source": peak_src}
+            traffic = None
+            tfile = ROOT / "profiles" / "ncu_traffic.json"          # DRAM bytes of the walk kernels from an `ncu --set full` capture of this command
+            if tfile.exists() and args.workload == "L" and info.world == 1:
+                try:
+                    traffic = float(json.loads(tfile.read_text())["walk_dram_bytes_per_launch"])
+                except Exception:
+                    traffic = None
+            walks = walk_stats["groups"] + walk_stats["individual"] if walk_stats["groups"] else nq
+            roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                        "kernel": "walk kernels of abb_walk_launch (walk_smem_kernel S1 + walk_global_kernel G1/GX + de-duplication passes)",
+                        "algorithmic_bytes_per_traversal": bytes_per, "bytes_estimated_from": f"oracle counters on {len(sample):,} sampled findings",
+                        "walk_ms_per_step": walk_ms_per_step, "peak_source": peak_src,
+                        "sharing": {"sources": nq, "traversals_executed": walks, "frontier_groups": walk_stats["groups"], "individual": walk_stats["individual"],
+                                    "note": "algorithmic bytes are counted per source, unshared (SURVEY 8d); sources with an identical depth-1 frontier share one "
+                                            "traversal and one result slice, so achieved can exceed the HBM peak - traffic is what DRAM actually moved"},
+                        }
+            roofline["sharing"]["result_nodes_stored"] = tot_nodes
+            roofline["sharing"]["result_nodes_referenced"] = int(walk.q_count[:nq].sum(dtype=torch.int64).item()) if len(batches) == 1 else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": info.world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",

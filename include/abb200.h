@@ -204,6 +204,9 @@ int64_t abb_launch_count(void);
  * abb_walk_launch / *_host call on this graph (CUDA events on the launch stream;
  * synchronises that stream). */
 float abb_last_walk_ms(abb_graph *g);
+/* {queries, frontier groups walked once, sources walked individually, sources eligible for sharing} of the most recent
+ * walk on this graph (zeros after the first when the batch was not de-duplicated).  Synchronises the device. */
+int abb_last_walk_stats(abb_graph *g, int64_t *out4);
 float abb_last_paths_ms(abb_graph *g);
 
 /* Host-buffer form (the call the Python store makes): H2D of the roots, the
