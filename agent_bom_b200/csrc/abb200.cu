@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -183,14 +184,15 @@ struct abb_graph {
     DevBuf dd_sig, dd_ssig, dd_q, dd_sq, dd_head, dd_gid, dd_hp, dd_glen, dd_goff, dd_arena, dd_memoff, dd_memsrc, dd_memstate, dd_indiv, dd_cnt, dd_tmp;
     DevBuf dd_gstart, dd_gcount, dd_gmaxd, dd_gflags, dd_ghist;
     bool dedup_enabled = true;
+    bool zero_copy = true;      // host-API walks write the node arena straight into pinned host memory when its size is known
     int64_t last_walk_queries = 0;
     bool last_walk_dedup = false;
-    int s1_cfg = 0;   // 0: 1024-slot hash / 512-entry queue, 1: 512/256 (more resident warps, earlier overflow)
+    int s1_cfg = 1;   // 1: 512-slot hash / 256-entry queue (more resident warps, earlier hand-off to G1; measured best), 0: 1024/512
     DevBuf identity_rank;
     // host-API staging
     DevBuf d_roots, d_root_off, d_targets, d_qstart, d_qcount, d_qmaxd, d_qflags, d_qestart, d_qecount, d_qhist;
     DevBuf d_nodes, d_parent, d_depth, d_edges, d_totals;
-    int64_t hint_nodes = 0, hint_edges = 0;
+    int64_t hint_nodes = 0, hint_edges = 0, hint_nq = 0, hint_last_nodes = 0;
     // graph-constant server fan-out table (built on first use)
     DevBuf srv_cred, srv_tool;
     bool srv_table_ready = false;
@@ -246,6 +248,7 @@ static int graph_finish_init(abb_graph *g) {
     }
     if (const char *e = getenv("ABB_DEDUP")) g->dedup_enabled = atoi(e) != 0;
     if (const char *e = getenv("ABB_S1_CFG")) g->s1_cfg = atoi(e);
+    if (const char *e = getenv("ABB_ZEROCOPY")) g->zero_copy = atoi(e) != 0;
     if (!g->v.rank) {
         if (int rc = g->identity_rank.ensure(static_cast<size_t>(n + 1) * 4)) return rc;
         std::vector<int32_t> id(static_cast<size_t>(n));
@@ -664,8 +667,11 @@ extern "C" int64_t abb_walk_result_h2d_bytes(const abb_walk_result *r) { return 
 extern "C" int64_t abb_walk_result_d2h_bytes(const abb_walk_result *r) { return r->d2h; }
 
 // stage inputs, run (re-run once if the arenas were too small), leave results on the device
+// `direct_nodes`: when the result size is known from the previous call, the walk kernels write the node arena
+// straight into that pinned host block (UVA), so the PCIe transfer of the largest output overlaps the traversal
+// instead of following it; if the estimate turns out too small the walk is re-run into a device arena.
 static int walk_device_stage(abb_graph *g, const abb_walk_spec *spec, const int32_t *roots, const int64_t *root_off, const int32_t *targets,
-                             int64_t nq, abb_walk_io *io_out, unsigned long long totals[2], int64_t *h2d) {
+                             int64_t nq, abb_walk_io *io_out, unsigned long long totals[2], int64_t *h2d, HostBlock *direct_nodes = nullptr) {
     cudaStream_t st = g->stream;
     const uint32_t fl = spec->flags;
     const int64_t n_roots = root_off ? root_off[nq] : nq;
@@ -688,8 +694,15 @@ static int walk_device_stage(abb_graph *g, const abb_walk_spec *spec, const int3
 
     int64_t node_cap = std::max<int64_t>({g->hint_nodes, nq * 8, 1 << 16});
     int64_t edge_cap = (fl & ABB_WALK_EDGES) ? std::max<int64_t>({g->hint_edges, nq * 16, 1 << 16}) : 0;
-    for (int attempt = 0; attempt < 2; attempt++) {
-        if (int rc = g->d_nodes.ensure(static_cast<size_t>(node_cap) * 4)) return rc;
+    bool direct = direct_nodes && g->zero_copy && g->hint_nodes > 0 && !(fl & (ABB_WALK_PARENTS | ABB_WALK_DEPTHS | ABB_WALK_EDGES));
+    if (direct) {
+        // same batch size as last time: its exact need plus a little; otherwise scale the last per-query average generously
+        node_cap = (nq == g->hint_nq) ? g->hint_last_nodes + g->hint_last_nodes / 64 + 4096
+                                      : static_cast<int64_t>(1.5 * static_cast<double>(g->hint_last_nodes) / std::max<int64_t>(g->hint_nq, 1) * nq) + 4096;
+        direct = direct_nodes->alloc(static_cast<size_t>(node_cap) * 4);
+    }
+    for (int attempt = 0; attempt < 3; attempt++) {
+        if (!direct) if (int rc = g->d_nodes.ensure(static_cast<size_t>(node_cap) * 4)) return rc;
         if (fl & ABB_WALK_PARENTS) if (int rc = g->d_parent.ensure(static_cast<size_t>(node_cap) * 4)) return rc;
         if (fl & ABB_WALK_DEPTHS) if (int rc = g->d_depth.ensure(static_cast<size_t>(node_cap) * 4)) return rc;
         if (fl & ABB_WALK_EDGES) if (int rc = g->d_edges.ensure(static_cast<size_t>(edge_cap) * 4)) return rc;
@@ -698,7 +711,8 @@ static int walk_device_stage(abb_graph *g, const abb_walk_spec *spec, const int3
         io.targets = (fl & ABB_WALK_TARGET) ? g->d_targets.as<int32_t>() : nullptr;
         io.q_start = g->d_qstart.as<int64_t>(); io.q_count = g->d_qcount.as<int32_t>(); io.q_maxd = g->d_qmaxd.as<int32_t>(); io.q_flags = g->d_qflags.as<int32_t>();
         io.q_estart = g->d_qestart.as<int64_t>(); io.q_ecount = g->d_qecount.as<int64_t>(); io.q_hist = g->d_qhist.as<uint32_t>();
-        io.nodes = g->d_nodes.as<int32_t>(); io.parent = g->d_parent.as<int32_t>(); io.depth = g->d_depth.as<int32_t>(); io.node_cap = node_cap;
+        io.nodes = direct ? direct_nodes->as<int32_t>() : g->d_nodes.as<int32_t>();
+        io.parent = g->d_parent.as<int32_t>(); io.depth = g->d_depth.as<int32_t>(); io.node_cap = node_cap;
         io.edges = g->d_edges.as<uint32_t>(); io.edge_cap = edge_cap; io.totals = g->d_totals.as<unsigned long long>();
         CUDA_TRY(cudaEventRecord(g->ev[0], st));
         if (int rc = enqueue_walk(g, spec, &io, st)) return rc;
@@ -713,8 +727,10 @@ static int walk_device_stage(abb_graph *g, const abb_walk_spec *spec, const int3
         *io_out = io;
         const bool fits = static_cast<int64_t>(totals[0]) <= node_cap && (!(fl & ABB_WALK_EDGES) || static_cast<int64_t>(totals[1]) <= edge_cap);
         g->hint_nodes = std::max<int64_t>(g->hint_nodes, static_cast<int64_t>(totals[0]));
+        g->hint_nq = nq; g->hint_last_nodes = static_cast<int64_t>(totals[0]);
         g->hint_edges = std::max<int64_t>(g->hint_edges, static_cast<int64_t>(totals[1]));
         if (fits) return ABB_OK;
+        if (direct) { direct_nodes->release(); direct = false; }     // estimate too small: fall back to a device arena
         node_cap = std::max<int64_t>(node_cap, static_cast<int64_t>(totals[0]));
         edge_cap = std::max<int64_t>(edge_cap, static_cast<int64_t>(totals[1]));
     }
@@ -722,7 +738,7 @@ static int walk_device_stage(abb_graph *g, const abb_walk_spec *spec, const int3
 }
 
 static int walk_collect(abb_graph *g, const abb_walk_spec *spec, const abb_walk_io &io, const unsigned long long totals[2], int64_t h2d,
-                        abb_walk_result **out, bool sync) {
+                        abb_walk_result **out, bool sync, HostBlock *direct_nodes = nullptr) {
     cudaStream_t st = g->stream;
     const uint32_t fl = spec->flags;
     const int64_t nq = io.n_queries;
@@ -730,7 +746,9 @@ static int walk_collect(abb_graph *g, const abb_walk_spec *spec, const abb_walk_
     r->nq = nq; r->flags = fl; r->total_nodes = static_cast<int64_t>(totals[0]); r->total_edges = (fl & ABB_WALK_EDGES) ? static_cast<int64_t>(totals[1]) : 0;
     r->h2d = h2d;
     const size_t q = static_cast<size_t>(nq), tn = static_cast<size_t>(r->total_nodes), te = static_cast<size_t>(r->total_edges);
-    bool ok = r->q_start.alloc(q * 8) && r->q_count.alloc(q * 4) && r->q_maxd.alloc(q * 4) && r->q_flags.alloc(q * 4) && r->nodes.alloc(tn * 4);
+    const bool have_nodes = direct_nodes && direct_nodes->p != nullptr;     // already written by the kernels over PCIe
+    if (have_nodes) { r->nodes = *direct_nodes; direct_nodes->p = nullptr; direct_nodes->bytes = 0; }
+    bool ok = r->q_start.alloc(q * 8) && r->q_count.alloc(q * 4) && r->q_maxd.alloc(q * 4) && r->q_flags.alloc(q * 4) && (have_nodes || r->nodes.alloc(tn * 4));
     if (fl & ABB_WALK_EDGES) ok = ok && r->q_estart.alloc(q * 8) && r->q_ecount.alloc(q * 8) && r->edges.alloc(te * 4);
     if (fl & ABB_WALK_HIST) ok = ok && r->q_hist.alloc(q * ABB_N_ENTITY_TYPES * 4);
     if (fl & ABB_WALK_PARENTS) ok = ok && r->parent.alloc(tn * 4);
@@ -743,7 +761,7 @@ static int walk_collect(abb_graph *g, const abb_walk_spec *spec, const abb_walk_
     cudaError_t e = cudaSuccess;
     auto acc = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
     acc(d2h(r->q_start, io.q_start, q * 8)); acc(d2h(r->q_count, io.q_count, q * 4)); acc(d2h(r->q_maxd, io.q_maxd, q * 4)); acc(d2h(r->q_flags, io.q_flags, q * 4));
-    acc(d2h(r->nodes, io.nodes, tn * 4));
+    if (have_nodes) r->d2h += static_cast<int64_t>(tn * 4); else acc(d2h(r->nodes, io.nodes, tn * 4));
     if (fl & ABB_WALK_EDGES) { acc(d2h(r->q_estart, io.q_estart, q * 8)); acc(d2h(r->q_ecount, io.q_ecount, q * 8)); acc(d2h(r->edges, io.edges, te * 4)); }
     if (fl & ABB_WALK_HIST) acc(d2h(r->q_hist, io.q_hist, q * ABB_N_ENTITY_TYPES * 4));
     if (fl & ABB_WALK_PARENTS) acc(d2h(r->parent, io.parent, tn * 4));
@@ -761,8 +779,11 @@ extern "C" int abb_walk_host(abb_graph *g, const abb_walk_spec *spec, const int3
     DeviceGuard dg(g->device);
     std::lock_guard<std::mutex> lk(g->mu);
     abb_walk_io io{}; unsigned long long totals[2] = {0, 0}; int64_t h2d = 0;
-    if (int rc = walk_device_stage(g, spec, roots, root_off, targets, n_queries, &io, totals, &h2d)) return rc;
-    return walk_collect(g, spec, io, totals, h2d, out, true);
+    HostBlock direct;
+    if (int rc = walk_device_stage(g, spec, roots, root_off, targets, n_queries, &io, totals, &h2d, &direct)) { direct.release(); return rc; }
+    int rc = walk_collect(g, spec, io, totals, h2d, out, true, &direct);
+    direct.release();
+    return rc;
 }
 
 // ------------------------------------------------------------------ exposure-path rows
@@ -1017,15 +1038,25 @@ extern "C" int abb_exposure_host(abb_graph *g, const int32_t *findings, int64_t 
     if (!g || !impact_out || !paths_out || n_findings < 0 || (n_findings && !findings)) return fail(ABB_ERR_ARG, "bad arguments");
     DeviceGuard dg(g->device);
     std::lock_guard<std::mutex> lk(g->mu);
+    const bool trace = getenv("ABB_TRACE") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    const auto t0 = now();
     abb_walk_spec spec = abb_spec_impact_of(max_depth);
     abb_walk_io io{}; unsigned long long totals[2] = {0, 0}; int64_t h2d = 0;
-    if (int rc = walk_device_stage(g, &spec, findings, nullptr, nullptr, n_findings, &io, totals, &h2d)) return rc;
+    HostBlock direct;
+    if (int rc = walk_device_stage(g, &spec, findings, nullptr, nullptr, n_findings, &io, totals, &h2d, &direct)) { direct.release(); return rc; }
+    const auto t1 = now();
     // result copies of the walk are enqueued (not waited for) before the path kernels; the findings are already resident
     abb_walk_result *wr = nullptr;
-    if (int rc = walk_collect(g, &spec, io, totals, h2d, &wr, false)) return rc;
+    if (int rc = walk_collect(g, &spec, io, totals, h2d, &wr, false, &direct)) { direct.release(); return rc; }
+    direct.release();
+    const auto t2 = now();
     abb_paths_result *pr = nullptr;
     int rc = paths_run(g, findings, g->d_roots.as<int32_t>(), n_findings, &pr);
     if (rc) { cudaStreamSynchronize(g->stream); abb_walk_result_free(wr); return rc; }
+    const auto t3 = now();
+    if (trace) fprintf(stderr, "[abb] exposure_host: stage+walk %.2f ms, enqueue result copies %.2f ms, paths (+ all copies) %.2f ms\n", ms(t0, t1), ms(t1, t2), ms(t2, t3));
     *impact_out = wr; *paths_out = pr;
     return ABB_OK;
 }

@@ -120,9 +120,9 @@ struct SmemStore {
 // ---------------------------------------------------------------- tier G store
 struct GlobalStore {
     static constexpr bool kGlobal = true;
-    uint32_t *bits; int32_t *queue; int32_t *par; int32_t *dep; int64_t cap;
+    uint32_t *bits; int32_t *queue; int32_t *par; int32_t *dep; int cap;   // dep == nullptr when no depth is ever read back
     __device__ void init(int) {}
-    __device__ __forceinline__ int64_t qcap() const { return cap; }
+    __device__ __forceinline__ int qcap() const { return cap; }
     __device__ __forceinline__ int max_level() const { return 0x7FFFFFF0; }
     __device__ __forceinline__ bool contains(int32_t k) const { return (bits[k >> 5] >> (k & 31)) & 1u; }
     __device__ __forceinline__ bool test_and_set(int32_t k, uint32_t &t) {
@@ -131,16 +131,16 @@ struct GlobalStore {
         uint32_t old = atomicOr(&bits[k >> 5], bit);
         return !(old & bit);
     }
-    __device__ __forceinline__ int32_t q_get(int64_t i) const { return queue[i]; }
-    __device__ __forceinline__ void put(int64_t i, int32_t node, int32_t p, uint32_t, int d) {
-        queue[i] = node; dep[i] = d; if (par) par[i] = p;
+    __device__ __forceinline__ int32_t q_get(int i) const { return queue[i]; }
+    __device__ __forceinline__ void put(int i, int32_t node, int32_t p, uint32_t, int d) {
+        queue[i] = node; if (dep) dep[i] = d; if (par) par[i] = p;
     }
-    __device__ __forceinline__ int32_t par_get(int64_t i) const { return par ? par[i] : -1; }
-    __device__ __forceinline__ int dep_get(int64_t i) const { return dep[i]; }
+    __device__ __forceinline__ int32_t par_get(int i) const { return par ? par[i] : -1; }
+    __device__ __forceinline__ int dep_get(int i) const { return dep ? dep[i] : 0; }
     __device__ __forceinline__ void unset(int32_t k, uint32_t) { atomicAnd(&bits[k >> 5], ~(1u << (k & 31))); }
-    __device__ void clear(int64_t count, int lane) {
+    __device__ void clear(int count, int lane) {
         __syncwarp();
-        for (int64_t i = lane; i < count; i += 32) bits[queue[i] >> 5] = 0u;
+        for (int i = lane; i < count; i += 32) bits[queue[i] >> 5] = 0u;
         __threadfence_block();
         __syncwarp();
     }
@@ -342,7 +342,7 @@ __device__ bool walk_one(const WalkArgs &A, Store &st, int64_t q, int lane, uint
                         stop = true;
                     }
                 }
-                rec_edges += __popc(pm);
+                if (BUDGET || (fl & ABB_WALK_EDGES)) rec_edges += __popc(pm);
                 // first lane among duplicates of a neighbour inside the chunk speaks for it
                 unsigned mm = __match_any_sync(FULL, pass ? c.nbr : (-2 - lane));
                 bool leader = pass && (__ffs(mm) - 1) == lane;
@@ -369,7 +369,8 @@ __device__ bool walk_one(const WalkArgs &A, Store &st, int64_t q, int lane, uint
                         return false;
                     }
                     if (isnew) st.put(tail + __popc(nm & lanemask_lt(lane)), c.nbr, static_cast<int32_t>(base + c.owner), tok, depth + 1);
-                    tail += cnt; nvis += cnt;
+                    tail += cnt;
+                    if (BUDGET) nvis += cnt;
                     if ((fl & ABB_WALK_TARGET) && __any_sync(FULL, isnew && c.nbr == target)) { qflags |= ABB_QFLAG_TARGET_FOUND; stop = true; }
                 }
                 __syncwarp();
@@ -510,9 +511,9 @@ __global__ void __launch_bounds__(128, 10) walk_global_kernel(const WalkArgs A) 
     GlobalStore st;
     st.bits = A.g_bitmap + slot * A.g_words;
     st.queue = A.g_queue + slot * A.g_qcap;
-    st.par = A.g_par ? A.g_par + slot * A.g_qcap : nullptr;
-    st.dep = A.g_dep + slot * A.g_qcap;
-    st.cap = A.g_qcap;
+    st.par = (A.g_par && (A.spec.flags & ABB_WALK_PARENTS)) ? A.g_par + slot * A.g_qcap : nullptr;
+    st.dep = (A.spec.flags & (ABB_WALK_DEPTHS | ABB_WALK_EDGES)) ? A.g_dep + slot * A.g_qcap : nullptr;
+    st.cap = static_cast<int>(A.g_qcap);
     const int64_t nq = A.nq_dev ? static_cast<int64_t>(*A.nq_dev) : A.nq;
     for (;;) {
         unsigned long long v = 0;
