@@ -226,7 +226,7 @@ static int graph_finish_init(abb_graph *g) {
     // tier G1: 40 warps per SM (latency-bound pointer chasing wants every warp it can get), queue bounded at 64K entries
     g->g_qcap = std::min<int64_t>(n + 4096, 1 << 16);
     g->g_slots = g->sm_count * 40;
-    if (const char *e = getenv("ABB_G1_WARPS_PER_SM")) g->g_slots = g->sm_count * std::max(4, std::min(40, atoi(e)));
+    if (const char *e = getenv("ABB_G1_WARPS_PER_SM")) g->g_slots = g->sm_count * std::max(4, std::min(48, atoi(e)));
     {
         const size_t sl = static_cast<size_t>(g->g_slots);
         if (int rc = g->g_bitmap.ensure(sl * g->g_words * 4)) return rc;
@@ -439,12 +439,18 @@ static int launch_smem_variant(const abb_graph *g, const WalkArgs &A, int64_t ma
     return fail(ABB_ERR_ARG, "unreachable");
 }
 
-static int launch_global_variant(const WalkArgs &A, int slots, bool meta, bool bud, cudaStream_t st) {
+static int launch_global_variant(const WalkArgs &A, int slots, int sm_count, bool meta, bool bud, cudaStream_t st) {
     const int blocks = std::max(1, slots / 4);
-    if (meta && bud) walk_global_kernel<true, true><<<blocks, 128, 0, st>>>(A);
-    else if (meta) walk_global_kernel<true, false><<<blocks, 128, 0, st>>>(A);
-    else if (bud) walk_global_kernel<false, true><<<blocks, 128, 0, st>>>(A);
-    else walk_global_kernel<false, false><<<blocks, 128, 0, st>>>(A);
+    const bool dense = slots > sm_count * 40;      // more than 40 warps per SM: the 40-register build (12 blocks of 4 warps per SM)
+    if (dense) {
+        if (meta && bud) walk_global_kernel<true, true, 12><<<blocks, 128, 0, st>>>(A);
+        else if (meta) walk_global_kernel<true, false, 12><<<blocks, 128, 0, st>>>(A);
+        else if (bud) walk_global_kernel<false, true, 12><<<blocks, 128, 0, st>>>(A);
+        else walk_global_kernel<false, false, 12><<<blocks, 128, 0, st>>>(A);
+    } else if (meta && bud) walk_global_kernel<true, true, 10><<<blocks, 128, 0, st>>>(A);
+    else if (meta) walk_global_kernel<true, false, 10><<<blocks, 128, 0, st>>>(A);
+    else if (bud) walk_global_kernel<false, true, 10><<<blocks, 128, 0, st>>>(A);
+    else walk_global_kernel<false, false, 10><<<blocks, 128, 0, st>>>(A);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return ABB_OK;
@@ -467,11 +473,11 @@ static int enqueue_tiers(abb_graph *g, WalkArgs A, int64_t max_items, unsigned l
     A.qlist = ov1; A.nq = 0; A.nq_dev = ctl + 1; A.ctl = ctl + 4; A.overflow = ov2;
     A.g_bitmap = g->g_bitmap.as<uint32_t>(); A.g_queue = g->g_queue.as<int32_t>(); A.g_par = g->g_par.as<int32_t>(); A.g_dep = g->g_dep.as<int32_t>();
     A.g_words = g->g_words; A.g_qcap = g->g_qcap;
-    if (int rc = launch_global_variant(A, g->g_slots, meta, bud, st)) return rc;
+    if (int rc = launch_global_variant(A, g->g_slots, g->sm_count, meta, bud, st)) return rc;
     A.qlist = ov2; A.nq_dev = ctl + 5; A.ctl = ctl + 8; A.overflow = nullptr;
     A.g_bitmap = g->x_bitmap.as<uint32_t>(); A.g_queue = g->x_queue.as<int32_t>(); A.g_par = g->x_par.as<int32_t>(); A.g_dep = g->x_dep.as<int32_t>();
     A.g_qcap = g->x_qcap;
-    return launch_global_variant(A, g->x_slots, meta, bud, st);
+    return launch_global_variant(A, g->x_slots, g->sm_count, meta, bud, st);
 }
 
 static int check_walk_io(const abb_walk_spec *spec, const abb_walk_io *io) {

@@ -323,11 +323,11 @@ __device__ bool walk_one(const WalkArgs &A, Store &st, int64_t q, int lane, uint
             exp_end = (base + 32 < lvl_end) ? base + 32 : lvl_end;
             // software pipeline: the next chunk's neighbour loads are in flight while this chunk's visited-set round trip resolves
             Cand nxt;
-            if (f.total) nxt = single ? fetch_single<NEED_META, false>(g, f.sF, f.dF, f.sR, f.total, lane) : fetch_cand<NEED_META, false>(g, f, lane);
+            if (f.total) nxt = single ? fetch_single<true, false>(g, f.sF, f.dF, f.sR, f.total, lane) : fetch_cand<true, false>(g, f, lane);
             for (uint32_t c0 = 0; c0 < f.total && !stop; c0 += 32) {
                 Cand c = nxt;
                 if (c0 + 32 < f.total)
-                    nxt = single ? fetch_single<NEED_META, false>(g, f.sF, f.dF, f.sR, f.total, c0 + 32 + lane) : fetch_cand<NEED_META, false>(g, f, c0 + 32 + lane);
+                    nxt = single ? fetch_single<true, false>(g, f.sF, f.dF, f.sR, f.total, c0 + 32 + lane) : fetch_cand<true, false>(g, f, c0 + 32 + lane);
                 bool pass = cand_passes(sp, c);
                 unsigned pm = __ballot_sync(FULL, pass);
                 if (BUDGET && sp.max_edges >= 0) {
@@ -343,9 +343,19 @@ __device__ bool walk_one(const WalkArgs &A, Store &st, int64_t q, int lane, uint
                     }
                 }
                 if (BUDGET || (fl & ABB_WALK_EDGES)) rec_edges += __popc(pm);
-                // first lane among duplicates of a neighbour inside the chunk speaks for it
-                unsigned mm = __match_any_sync(FULL, pass ? c.nbr : (-2 - lane));
-                bool leader = pass && (__ffs(mm) - 1) == lane;
+                // The first lane among duplicates of a neighbour inside the chunk speaks for it.  When the whole chunk comes
+                // from ONE row of an unfiltered walk, "first of its neighbour in the row" is the precomputed FIRST_PAIR bit:
+                // a later duplicate can never discover anything (its first occurrence already did), so no match.any is needed.
+                bool leader;
+                const int owner0 = __shfl_sync(FULL, c.owner, 0);      // every lane takes part: no shuffle inside a short-circuit
+                const bool same_owner = __all_sync(FULL, !c.active || c.owner == owner0);
+                const bool one_row = !NEED_META && sp.direction != ABB_DIR_BOTH && (single || same_owner);
+                if (one_row) {
+                    leader = pass && (c.meta & ABB_META_FIRST_PAIR);
+                } else {
+                    unsigned mm = __match_any_sync(FULL, pass ? c.nbr : (-2 - lane));
+                    leader = pass && (__ffs(mm) - 1) == lane;
+                }
                 bool isnew = false;
                 uint32_t tok = NO_TOK;
                 if (BUDGET && sp.max_nodes >= 0) {
@@ -503,8 +513,8 @@ __global__ void __launch_bounds__(WARPS * 32) walk_smem_kernel(const WalkArgs A)
     }
 }
 
-template <bool NEED_META, bool BUDGET>
-__global__ void __launch_bounds__(128, 10) walk_global_kernel(const WalkArgs A) {
+template <bool NEED_META, bool BUDGET, int MIN_BLOCKS>
+__global__ void __launch_bounds__(128, MIN_BLOCKS) walk_global_kernel(const WalkArgs A) {
     __shared__ uint32_t s_hist[4][ABB_N_ENTITY_TYPES];
     const int lane = threadIdx.x & 31;
     const int64_t slot = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
