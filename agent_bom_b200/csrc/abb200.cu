@@ -171,6 +171,8 @@ struct abb_graph {
     int sm_count = 148;
     std::mutex mu;                    // serialises use of the shared workspace
     cudaStream_t stream = nullptr;    // host-API stream
+    cudaStream_t copy_stream = nullptr;   // result copies that may overlap later kernels of the same call
+    cudaEvent_t ev_copy = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool walk_timed = false, paths_timed = false;
     // tier bookkeeping
@@ -219,6 +221,8 @@ static int graph_finish_init(abb_graph *g) {
     CUDA_TRY(cudaGetDeviceProperties(&prop, g->device));
     g->sm_count = prop.multiProcessorCount;
     CUDA_TRY(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&g->copy_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&g->ev_copy, cudaEventDisableTiming));
     for (auto &e : g->ev) CUDA_TRY(cudaEventCreate(&e));
     if (int rc = g->ctl.ensure(64 * sizeof(unsigned long long))) return rc;
     const int64_t n = g->v.n;
@@ -344,6 +348,8 @@ extern "C" void abb_graph_free(abb_graph *g) {
     if (!g) return;
     DeviceGuard dg(g->device);
     if (g->stream) { cudaStreamSynchronize(g->stream); cudaStreamDestroy(g->stream); }
+    if (g->copy_stream) { cudaStreamSynchronize(g->copy_stream); cudaStreamDestroy(g->copy_stream); }
+    if (g->ev_copy) cudaEventDestroy(g->ev_copy);
     for (auto &e : g->ev) if (e) cudaEventDestroy(e);
     for (DevBuf *b : {&g->ctl, &g->ov1, &g->ov2, &g->g_bitmap, &g->g_queue, &g->g_par, &g->g_dep, &g->x_bitmap, &g->x_queue, &g->x_par, &g->x_dep, &g->dd_sig, &g->dd_ssig, &g->dd_q, &g->dd_sq, &g->dd_head, &g->dd_gid, &g->dd_hp, &g->dd_glen, &g->dd_goff, &g->dd_arena, &g->dd_memoff, &g->dd_memsrc, &g->dd_memstate, &g->dd_indiv, &g->dd_cnt, &g->dd_tmp, &g->dd_gstart, &g->dd_gcount, &g->dd_gmaxd, &g->dd_gflags, &g->dd_ghist, &g->identity_rank, &g->d_roots, &g->d_root_off,
                       &g->d_targets, &g->d_qstart, &g->d_qcount, &g->d_qmaxd, &g->d_qflags, &g->d_qestart, &g->d_qecount, &g->d_qhist, &g->d_nodes,
@@ -743,9 +749,16 @@ static int walk_device_stage(abb_graph *g, const abb_walk_spec *spec, const int3
     return fail(ABB_ERR_CAPACITY, "walk arenas still too small after resize");
 }
 
+// sync == false: the copies go to the graph's copy stream (ordered after everything enqueued so far on the main stream)
+// so that kernels enqueued next on the main stream overlap them; the caller synchronises the copy stream.
 static int walk_collect(abb_graph *g, const abb_walk_spec *spec, const abb_walk_io &io, const unsigned long long totals[2], int64_t h2d,
                         abb_walk_result **out, bool sync, HostBlock *direct_nodes = nullptr) {
     cudaStream_t st = g->stream;
+    if (!sync) {
+        CUDA_TRY(cudaEventRecord(g->ev_copy, g->stream));
+        CUDA_TRY(cudaStreamWaitEvent(g->copy_stream, g->ev_copy, 0));
+        st = g->copy_stream;
+    }
     const uint32_t fl = spec->flags;
     const int64_t nq = io.n_queries;
     abb_walk_result *r = new abb_walk_result();
@@ -1060,7 +1073,9 @@ extern "C" int abb_exposure_host(abb_graph *g, const int32_t *findings, int64_t 
     const auto t2 = now();
     abb_paths_result *pr = nullptr;
     int rc = paths_run(g, findings, g->d_roots.as<int32_t>(), n_findings, &pr);
+    cudaError_t ce = cudaStreamSynchronize(g->copy_stream);       // the walk's result copies overlapped the path pipeline
     if (rc) { cudaStreamSynchronize(g->stream); abb_walk_result_free(wr); return rc; }
+    if (ce != cudaSuccess) { abb_walk_result_free(wr); abb_paths_result_free(pr); return fail(ABB_ERR_CUDA, "walk D2H failed: %s", cudaGetErrorString(ce)); }
     const auto t3 = now();
     if (trace) fprintf(stderr, "[abb] exposure_host: stage+walk %.2f ms, enqueue result copies %.2f ms, paths (+ all copies) %.2f ms\n", ms(t0, t1), ms(t1, t2), ms(t2, t3));
     *impact_out = wr; *paths_out = pr;

@@ -192,7 +192,8 @@ typedef struct abb_walk_io {
     unsigned long long *totals; /* device [2]: nodes / edges needed; zeroed by the launch */
 } abb_walk_io;
 
-/* Enqueue the walk on `stream` (a cudaStream_t, NULL = default stream).  Asynchronous. */
+/* Enqueue the walk on `stream` (a cudaStream_t, NULL = default stream).  Asynchronous.  One walk may be in flight per
+ * graph handle (the tiers share the handle's scratch); serialise callers or use one handle per stream. */
 int abb_walk_launch(abb_graph *g, const abb_walk_spec *spec, const abb_walk_io *io, void *stream);
 /* 64-bit signature of each single-source query's depth-1 frontier (device arrays).  Sources with equal signatures
  * share one traversal when walked in the same batch, so multi-GPU runs shard the source list by signature
