@@ -321,13 +321,29 @@ __device__ bool walk_one(const WalkArgs &A, Store &st, int64_t q, int lane, uint
                 f = load_frontier(g, sp.direction, u, fvalid);
             }
             exp_end = (base + 32 < lvl_end) ? base + 32 : lvl_end;
+            // Long rows (>= 40 candidates per frontier node on average) are consumed row by row: a segment is one node's
+            // rows, fetched without the flattening search and always a single-row chunk.  Short rows stay flattened so
+            // that 32 lanes still see 32 candidates.  Either way candidates are met in (queue, row) order.
+            const int nvalid = static_cast<int>((lvl_end - base) < 32 ? (lvl_end - base) : 32);
+            const bool row_mode = !single && f.total >= 40u * static_cast<uint32_t>(nvalid);
+            const int nseg = row_mode ? nvalid : 1;
+            for (int seg = 0; seg < nseg && !stop; seg++) {
+            uint32_t sF = f.sF, dF = f.dF, sR = f.sR, total = f.total;
+            bool seg_single = single;
+            if (row_mode) {
+                sF = __shfl_sync(FULL, f.sF, seg); dF = __shfl_sync(FULL, f.dF, seg); sR = __shfl_sync(FULL, f.sR, seg);
+                const uint32_t ex = __shfl_sync(FULL, f.excl, seg), exn = __shfl_sync(FULL, f.excl, (seg + 1) & 31);
+                total = (seg == 31 ? f.total : exn) - ex;
+                seg_single = true;
+            }
             // software pipeline: the next chunk's neighbour loads are in flight while this chunk's visited-set round trip resolves
             Cand nxt;
-            if (f.total) nxt = single ? fetch_single<true, false>(g, f.sF, f.dF, f.sR, f.total, lane) : fetch_cand<true, false>(g, f, lane);
-            for (uint32_t c0 = 0; c0 < f.total && !stop; c0 += 32) {
+            if (total) nxt = seg_single ? fetch_single<true, false>(g, sF, dF, sR, total, lane) : fetch_cand<true, false>(g, f, lane);
+            for (uint32_t c0 = 0; c0 < total && !stop; c0 += 32) {
                 Cand c = nxt;
-                if (c0 + 32 < f.total)
-                    nxt = single ? fetch_single<true, false>(g, f.sF, f.dF, f.sR, f.total, c0 + 32 + lane) : fetch_cand<true, false>(g, f, c0 + 32 + lane);
+                if (c0 + 32 < total)
+                    nxt = seg_single ? fetch_single<true, false>(g, sF, dF, sR, total, c0 + 32 + lane) : fetch_cand<true, false>(g, f, c0 + 32 + lane);
+                if (row_mode) c.owner = seg;
                 bool pass = cand_passes(sp, c);
                 unsigned pm = __ballot_sync(FULL, pass);
                 if (BUDGET && sp.max_edges >= 0) {
@@ -349,7 +365,7 @@ __device__ bool walk_one(const WalkArgs &A, Store &st, int64_t q, int lane, uint
                 bool leader;
                 const int owner0 = __shfl_sync(FULL, c.owner, 0);      // every lane takes part: no shuffle inside a short-circuit
                 const bool same_owner = __all_sync(FULL, !c.active || c.owner == owner0);
-                const bool one_row = !NEED_META && sp.direction != ABB_DIR_BOTH && (single || same_owner);
+                const bool one_row = !NEED_META && sp.direction != ABB_DIR_BOTH && (seg_single || same_owner);
                 if (one_row) {
                     leader = pass && (c.meta & ABB_META_FIRST_PAIR);
                 } else {
@@ -385,6 +401,7 @@ __device__ bool walk_one(const WalkArgs &A, Store &st, int64_t q, int lane, uint
                 }
                 __syncwarp();
             }
+            }   // segments
         }
         depth++;
         lvl_begin = lvl_end; lvl_end = tail;
