@@ -321,87 +321,70 @@ __device__ bool walk_one(const WalkArgs &A, Store &st, int64_t q, int lane, uint
                 f = load_frontier(g, sp.direction, u, fvalid);
             }
             exp_end = (base + 32 < lvl_end) ? base + 32 : lvl_end;
-            // Long rows (>= 40 candidates per frontier node on average) are consumed row by row: a segment is one node's
-            // rows, fetched without the flattening search and always a single-row chunk.  Short rows stay flattened so
-            // that 32 lanes still see 32 candidates.  Either way candidates are met in (queue, row) order.
-            const int nvalid = static_cast<int>((lvl_end - base) < 32 ? (lvl_end - base) : 32);
-            const bool row_mode = !single && f.total >= 40u * static_cast<uint32_t>(nvalid);
-            const int nseg = row_mode ? nvalid : 1;
-            for (int seg = 0; seg < nseg && !stop; seg++) {
-                uint32_t sF = f.sF, dF = f.dF, sR = f.sR, total = f.total;
-                bool seg_single = single;
-                if (row_mode) {
-                    sF = __shfl_sync(FULL, f.sF, seg); dF = __shfl_sync(FULL, f.dF, seg); sR = __shfl_sync(FULL, f.sR, seg);
-                    const uint32_t ex = __shfl_sync(FULL, f.excl, seg), exn = __shfl_sync(FULL, f.excl, (seg + 1) & 31);
-                    total = (seg == 31 ? f.total : exn) - ex;
-                    seg_single = true;
+            // software pipeline: the next chunk's neighbour loads are in flight while this chunk's visited-set round trip resolves
+            Cand nxt;
+            if (f.total) nxt = single ? fetch_single<true, false>(g, f.sF, f.dF, f.sR, f.total, lane) : fetch_cand<true, false>(g, f, lane);
+            for (uint32_t c0 = 0; c0 < f.total && !stop; c0 += 32) {
+                Cand c = nxt;
+                if (c0 + 32 < f.total)
+                    nxt = single ? fetch_single<true, false>(g, f.sF, f.dF, f.sR, f.total, c0 + 32 + lane) : fetch_cand<true, false>(g, f, c0 + 32 + lane);
+                bool pass = cand_passes(sp, c);
+                unsigned pm = __ballot_sync(FULL, pass);
+                if (BUDGET && sp.max_edges >= 0) {
+                    // edge_count += 1; if edge_count > max_edges: truncated, break  (container.py:507-510)
+                    long long my_ec = rec_edges + __popc(pm & (lanemask_lt(lane) | (1u << lane)));
+                    unsigned over = __ballot_sync(FULL, pass && my_ec > sp.max_edges);
+                    if (over) {
+                        int fo = __ffs(over) - 1;
+                        pass = pass && lane < fo;
+                        pm &= lanemask_lt(fo);
+                        qflags |= ABB_QFLAG_TRUNCATED;
+                        stop = true;
+                    }
                 }
-                // software pipeline: the next chunk's neighbour loads are in flight while this chunk's visited-set round trip resolves
-                Cand nxt;
-                if (total) nxt = seg_single ? fetch_single<true, false>(g, sF, dF, sR, total, lane) : fetch_cand<true, false>(g, f, lane);
-                for (uint32_t c0 = 0; c0 < total && !stop; c0 += 32) {
-                    Cand c = nxt;
-                    if (c0 + 32 < total)
-                        nxt = seg_single ? fetch_single<true, false>(g, sF, dF, sR, total, c0 + 32 + lane) : fetch_cand<true, false>(g, f, c0 + 32 + lane);
-                    if (row_mode) c.owner = seg;
-                    bool pass = cand_passes(sp, c);
-                    unsigned pm = __ballot_sync(FULL, pass);
-                    if (BUDGET && sp.max_edges >= 0) {
-                        // edge_count += 1; if edge_count > max_edges: truncated, break  (container.py:507-510)
-                        long long my_ec = rec_edges + __popc(pm & (lanemask_lt(lane) | (1u << lane)));
-                        unsigned over = __ballot_sync(FULL, pass && my_ec > sp.max_edges);
-                        if (over) {
-                            int fo = __ffs(over) - 1;
-                            pass = pass && lane < fo;
-                            pm &= lanemask_lt(fo);
-                            qflags |= ABB_QFLAG_TRUNCATED;
-                            stop = true;
-                        }
-                    }
-                    if (BUDGET || (fl & ABB_WALK_EDGES)) rec_edges += __popc(pm);
-                    // The first lane among duplicates of a neighbour inside the chunk speaks for it.  When the whole chunk comes
-                    // from ONE row of an unfiltered walk, "first of its neighbour in the row" is the precomputed FIRST_PAIR bit:
-                    // a later duplicate can never discover anything (its first occurrence already did), so no match.any is needed.
-                    bool leader;
-                    const int owner0 = __shfl_sync(FULL, c.owner, 0);      // every lane takes part: no shuffle inside a short-circuit
-                    const bool same_owner = __all_sync(FULL, !c.active || c.owner == owner0);
-                    const bool one_row = !NEED_META && sp.direction != ABB_DIR_BOTH && (seg_single || same_owner);
-                    if (one_row) {
-                        leader = pass && (c.meta & ABB_META_FIRST_PAIR);
-                    } else {
-                        unsigned mm = __match_any_sync(FULL, pass ? c.nbr : (-2 - lane));
-                        leader = pass && (__ffs(mm) - 1) == lane;
-                    }
-                    bool isnew = false;
-                    uint32_t tok = NO_TOK;
-                    if (BUDGET && sp.max_nodes >= 0) {
-                        // if neighbor in visited: continue; if len(visited) >= max_nodes: truncated; continue (container.py:515-519)
-                        bool unseen = leader && !st.contains(c.nbr);
-                        unsigned um = __ballot_sync(FULL, unseen);
-                        long long before = nvis + __popc(um & lanemask_lt(lane));
-                        bool allowed = unseen && before < sp.max_nodes;
-                        if (um && (nvis + __popc(um)) > sp.max_nodes) qflags |= ABB_QFLAG_TRUNCATED;
-                        // a non-leader duplicate of a denied neighbour is denied too (still unvisited, budget still full)
-                        if (allowed) isnew = st.test_and_set(c.nbr, tok);
-                    } else if (leader) {
-                        isnew = st.test_and_set(c.nbr, tok);
-                    }
-                    unsigned nm = __ballot_sync(FULL, isnew);
-                    int cnt = __popc(nm);
-                    if (cnt) {
-                        if (tail + cnt > st.qcap()) {
-                            if (isnew) st.unset(c.nbr, tok);   // inserted this chunk but never queued
-                            st.clear(tail, lane);
-                            return false;
-                        }
-                        if (isnew) st.put(tail + __popc(nm & lanemask_lt(lane)), c.nbr, static_cast<int32_t>(base + c.owner), tok, depth + 1);
-                        tail += cnt;
-                        if (BUDGET) nvis += cnt;
-                        if ((fl & ABB_WALK_TARGET) && __any_sync(FULL, isnew && c.nbr == target)) { qflags |= ABB_QFLAG_TARGET_FOUND; stop = true; }
-                    }
-                    __syncwarp();
+                if (BUDGET || (fl & ABB_WALK_EDGES)) rec_edges += __popc(pm);
+                // The first lane among duplicates of a neighbour inside the chunk speaks for it.  When the whole chunk comes
+                // from ONE row of an unfiltered walk, "first of its neighbour in the row" is the precomputed FIRST_PAIR bit:
+                // a later duplicate can never discover anything (its first occurrence already did), so no match.any is needed.
+                bool leader;
+                const int owner0 = __shfl_sync(FULL, c.owner, 0);      // every lane takes part: no shuffle inside a short-circuit
+                const bool same_owner = __all_sync(FULL, !c.active || c.owner == owner0);
+                const bool one_row = !NEED_META && sp.direction != ABB_DIR_BOTH && (single || same_owner);
+                if (one_row) {
+                    leader = pass && (c.meta & ABB_META_FIRST_PAIR);
+                } else {
+                    unsigned mm = __match_any_sync(FULL, pass ? c.nbr : (-2 - lane));
+                    leader = pass && (__ffs(mm) - 1) == lane;
                 }
-            }   // segments
+                bool isnew = false;
+                uint32_t tok = NO_TOK;
+                if (BUDGET && sp.max_nodes >= 0) {
+                    // if neighbor in visited: continue; if len(visited) >= max_nodes: truncated; continue (container.py:515-519)
+                    bool unseen = leader && !st.contains(c.nbr);
+                    unsigned um = __ballot_sync(FULL, unseen);
+                    long long before = nvis + __popc(um & lanemask_lt(lane));
+                    bool allowed = unseen && before < sp.max_nodes;
+                    if (um && (nvis + __popc(um)) > sp.max_nodes) qflags |= ABB_QFLAG_TRUNCATED;
+                    // a non-leader duplicate of a denied neighbour is denied too (still unvisited, budget still full)
+                    if (allowed) isnew = st.test_and_set(c.nbr, tok);
+                } else if (leader) {
+                    isnew = st.test_and_set(c.nbr, tok);
+                }
+                unsigned nm = __ballot_sync(FULL, isnew);
+                int cnt = __popc(nm);
+                if (cnt) {
+                    if (tail + cnt > st.qcap()) {
+                        if (isnew) st.unset(c.nbr, tok);   // inserted this chunk but never queued
+                        st.clear(tail, lane);
+                        return false;
+                    }
+                    if (isnew) st.put(tail + __popc(nm & lanemask_lt(lane)), c.nbr, static_cast<int32_t>(base + c.owner), tok, depth + 1);
+                    tail += cnt;
+                    if (BUDGET) nvis += cnt;
+                    if ((fl & ABB_WALK_TARGET) && __any_sync(FULL, isnew && c.nbr == target)) { qflags |= ABB_QFLAG_TARGET_FOUND; stop = true; }
+                }
+                __syncwarp();
+            }
         }
         depth++;
         lvl_begin = lvl_end; lvl_end = tail;
