@@ -61,6 +61,7 @@ class UnifiedGraph:
         self._edge_index: dict[tuple[str, str, str], int] = {}
         self.attack_paths: list[AttackPath] = []
         self.interaction_risks: list[Any] = []
+        self.unhandled_sections: list[str] = []      # report sections the light builder did not model (graph/builder.py)
         self.scan_id, self.tenant_id = scan_id, tenant_id
         self.created_at = created_at or _now_iso()
         self.device = device

@@ -355,11 +355,62 @@ def estate_identity():
     print(f"-> {path} {path.stat().st_size / 1024:.0f} KiB")
 
 
+def builder_identity():
+    """Pin agent_bom_b200.graph.build_unified_graph_from_report against the reference builder on the same reports.
+
+    The two keyword tables the reference keeps outside its graph package (tool classification, credential-key patterns)
+    are captured as lookup tables of the reference's own answers for the names occurring in each report."""
+    from agent_bom.constants import is_credential_key
+    from agent_bom.risk_analyzer import classify_tool
+    from agent_bom_b200 import estate as est_mod
+
+    inv = json.loads((REF / "examples" / "agent-mesh-inventory.json").read_text())
+    rows, k = [], 0
+    for agent in inv.get("agents", []):
+        for server in agent.get("mcp_servers", []):
+            for pkg in server.get("packages", []):
+                rows.append({"vulnerability_id": f"CVE-2030-{k:04d}", "severity": ("critical", "high", "medium", "low")[k % 4], "package": pkg.get("name", ""),
+                             "package_name": pkg.get("name", ""), "package_version": pkg.get("version", ""), "ecosystem": pkg.get("ecosystem", ""),
+                             "risk_score": (k % 7) * 1.5})
+                k += 1
+    mesh = dict(inv, blast_radius=rows)
+    reports = [
+        ("estate-dense", est_mod.generate(40, 3, est_mod.Knobs.dense(4, 8, 2), exact_rank=True).report_json()),
+        ("estate-shipped", est_mod.generate(90, 3, est_mod.Knobs(), exact_rank=True).report_json()),
+        ("mesh-inventory", inv),
+        ("mesh-inventory+blast-overlay", mesh),
+    ]
+    docs = []
+    for label, report in reports:
+        g = build_unified_graph_from_report(json.loads(json.dumps(report)))
+        tool_caps, cred_keys = {}, []
+        for agent in report.get("agents", []):
+            for server in agent.get("mcp_servers", []):
+                for tool in server.get("tools", []):
+                    key = f"{tool.get('name', '')}|#|{tool.get('description', '')}"
+                    tool_caps[key] = [c.value for c in classify_tool(str(tool.get("name", "")), str(tool.get("description", "")))]
+                env = server.get("env", {})
+                if isinstance(env, dict):
+                    cred_keys.extend(k2 for k2 in env if is_credential_key(k2))
+        docs.append({
+            "label": label, "report": report, "tool_caps": tool_caps, "cred_keys": sorted(set(cred_keys)),
+            "nodes": [[n.id, enum_value(n.entity_type), n.label, n.severity, float(n.risk_score or 0.0)] for n in g.nodes.values()],
+            "edges": [[e.source, e.target, enum_value(e.relationship), e.direction, bool(e.traversable)] for e in g.edges],
+        })
+        print(f"builder_identity {label}: {len(g.nodes)} nodes {len(g.edges)} edges")
+    path = OUT / "identity" / "builder_identity.json.gz"
+    with gzip.GzipFile(path, "wb", mtime=0) as fh:
+        fh.write(json.dumps(docs, separators=(",", ":"), sort_keys=True).encode())
+    print(f"-> {path} {path.stat().st_size / 1024:.0f} KiB")
+
+
 def main():
     if "--identity-only" in sys.argv:
         estate_identity()
+        builder_identity()
         return
     estate_identity()
+    builder_identity()
     rng = random.Random(20260921)
     run_battery("kat_schema", kat_schema(), rng, small=True)
     run_battery("kat_directed", kat_directed(), rng, small=True)
