@@ -128,6 +128,16 @@ EXPORTS = {
     "abb_paths_result_h2d_bytes": (i64, [vp]),
     "abb_paths_result_d2h_bytes": (i64, [vp]),
     "abb_paths_result_free": (None, [vp]),
+    "abb_paths_rank_host": (C.c_int, [vp, vp, i64, vp, vp, i64, vp, vp, i64, i64, C.POINTER(vp)]),
+    "abb_rank_result_total": (i64, [vp]),
+    "abb_rank_result_count": (i64, [vp]),
+    "abb_rank_result_hops": (vp, [vp]),
+    "abb_rank_result_rels": (vp, [vp]),
+    "abb_rank_result_ncred": (vp, [vp]),
+    "abb_rank_result_ntool": (vp, [vp]),
+    "abb_rank_result_risk_rank": (vp, [vp]),
+    "abb_rank_result_row": (vp, [vp]),
+    "abb_rank_result_free": (None, [vp]),
     "abb_exposure_host": (C.c_int, [vp, vp, i64, i32, C.POINTER(vp), C.POINTER(vp)]),
     "abb_dependency_reach_host": (C.c_int, [vp, vp, i64, u32, u32, C.POINTER(vp)]),
     "abb_reach_n_packages": (i64, [vp]),

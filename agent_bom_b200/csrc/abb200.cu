@@ -1052,6 +1052,109 @@ extern "C" int abb_paths_host(abb_graph *g, const int32_t *findings, int64_t n_f
     return paths_run(g, findings, nullptr, n_findings, out);
 }
 
+// ------------------------------------------------------------------ ranked page of exposure-path rows
+struct abb_rank_result {
+    int64_t total = 0, count = 0;
+    std::vector<int32_t> hops, ncred, ntool;
+    std::vector<int8_t> rels;
+    std::vector<uint32_t> risk_rank;
+    std::vector<int64_t> row;
+};
+extern "C" void abb_rank_result_free(abb_rank_result *r) { delete r; }
+extern "C" int64_t abb_rank_result_total(const abb_rank_result *r) { return r->total; }
+extern "C" int64_t abb_rank_result_count(const abb_rank_result *r) { return r->count; }
+extern "C" const int32_t *abb_rank_result_hops(const abb_rank_result *r) { return r->hops.data(); }
+extern "C" const int8_t *abb_rank_result_rels(const abb_rank_result *r) { return r->rels.data(); }
+extern "C" const int32_t *abb_rank_result_ncred(const abb_rank_result *r) { return r->ncred.data(); }
+extern "C" const int32_t *abb_rank_result_ntool(const abb_rank_result *r) { return r->ntool.data(); }
+extern "C" const uint32_t *abb_rank_result_risk_rank(const abb_rank_result *r) { return r->risk_rank.data(); }
+extern "C" const int64_t *abb_rank_result_row(const abb_rank_result *r) { return r->row.data(); }
+
+struct ScopedDev {   // scoped device allocation for the ranking pass (sizes follow the row count)
+    void *p = nullptr;
+    ~ScopedDev() { if (p) cudaFree(p); }
+    int alloc(size_t bytes) {
+        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 16);
+        return e == cudaSuccess ? ABB_OK : fail(ABB_ERR_NOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+    }
+    template <class T> T *as() const { return static_cast<T *>(p); }
+};
+
+extern "C" int abb_paths_rank_host(abb_graph *g, const int32_t *findings, int64_t n_findings, const int32_t *base_id, const uint32_t *risk_rank, int64_t n_base,
+                                   const int32_t *ncu, const int32_t *ntu, int64_t offset, int64_t limit, abb_rank_result **out) {
+    if (!g || !out || n_findings < 0 || offset < 0 || limit < 0 || n_base <= 0 || !risk_rank || !ncu || !ntu || (n_findings && (!findings || !base_id)))
+        return fail(ABB_ERR_ARG, "bad arguments");
+    DeviceGuard dg(g->device);
+    std::lock_guard<std::mutex> lk(g->mu);
+    cudaStream_t st = g->stream;
+    const int64_t nf = n_findings, n = g->v.n;
+    if (int rc = g->p_findings.ensure(static_cast<size_t>(nf + 1) * 4)) return rc;
+    if (int rc = g->p_off.ensure(static_cast<size_t>(nf + 1) * 8)) return rc;
+    ScopedDev d_base, d_tab, d_ncu, d_ntu;
+    if (int rc = d_base.alloc(static_cast<size_t>(nf + 1) * 4)) return rc;
+    if (int rc = d_tab.alloc(static_cast<size_t>(n_base) * 75 * 4)) return rc;
+    if (int rc = d_ncu.alloc(static_cast<size_t>(n + 1) * 4)) return rc;
+    if (int rc = d_ntu.alloc(static_cast<size_t>(n + 1) * 4)) return rc;
+    if (nf) {
+        CUDA_TRY(cudaMemcpyAsync(g->p_findings.p, findings, static_cast<size_t>(nf) * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(d_base.p, base_id, static_cast<size_t>(nf) * 4, cudaMemcpyHostToDevice, st));
+    }
+    CUDA_TRY(cudaMemcpyAsync(d_tab.p, risk_rank, static_cast<size_t>(n_base) * 75 * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_ncu.p, ncu, static_cast<size_t>(n) * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_ntu.p, ntu, static_cast<size_t>(n) * 4, cudaMemcpyHostToDevice, st));
+    abb_paths_io io{};
+    io.n_findings = nf; io.findings = g->p_findings.as<int32_t>(); io.f_off = g->p_off.as<int64_t>();
+    if (int rc = enqueue_paths_count(g, &io, st)) return rc;
+    int64_t R = 0;
+    CUDA_TRY(cudaMemcpyAsync(&R, io.f_off + nf, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (R >= (1ll << 32) - 1) return fail(ABB_ERR_CAPACITY, "more than 2^32 exposure-path rows in one ranking batch");
+    abb_rank_result *r = new abb_rank_result();
+    r->total = R;
+    const int64_t first = std::min(offset, R), count = std::min(limit, R - first);
+    r->count = count;
+    if (R == 0 || count == 0) { *out = r; return ABB_OK; }
+    ScopedDev k1, k2, v1, v2, tmp, o_hops, o_rels, o_nc, o_nt, o_rank, o_row;
+    int rc = k1.alloc(static_cast<size_t>(R) * 8);
+    if (!rc) rc = k2.alloc(static_cast<size_t>(R) * 8);
+    if (!rc) rc = v1.alloc(static_cast<size_t>(R) * 4);
+    if (!rc) rc = v2.alloc(static_cast<size_t>(R) * 4);
+    if (!rc) rc = o_hops.alloc(static_cast<size_t>(count) * 16);
+    if (!rc) rc = o_rels.alloc(static_cast<size_t>(count) * 4);
+    if (!rc) rc = o_nc.alloc(static_cast<size_t>(count) * 4);
+    if (!rc) rc = o_nt.alloc(static_cast<size_t>(count) * 4);
+    if (!rc) rc = o_rank.alloc(static_cast<size_t>(count) * 4);
+    if (!rc) rc = o_row.alloc(static_cast<size_t>(count) * 8);
+    if (rc) { delete r; return rc; }
+    PathsArgs A = g->paths_args;
+    RankArgs RA{d_base.as<int32_t>(), d_tab.as<uint32_t>(), d_ncu.as<int32_t>(), d_ntu.as<int32_t>(), k1.as<unsigned long long>(), v1.as<uint32_t>()};
+    rank_keys_kernel<<<warp_grid(g, (nf + 31) / 32), 256, 0, st>>>(A, RA); g_launches++;
+    size_t tb = 0;
+    cudaError_t ce = cub::DeviceRadixSort::SortPairs(nullptr, tb, k1.as<unsigned long long>(), k2.as<unsigned long long>(), v1.as<uint32_t>(), v2.as<uint32_t>(),
+                                                     static_cast<int>(R), 0, 64, st);
+    if (ce == cudaSuccess && !(rc = tmp.alloc(tb)))
+        ce = cub::DeviceRadixSort::SortPairs(tmp.p, tb, k1.as<unsigned long long>(), k2.as<unsigned long long>(), v1.as<uint32_t>(), v2.as<uint32_t>(),
+                                             static_cast<int>(R), 0, 64, st);
+    g_launches++;
+    if (rc || ce != cudaSuccess) { delete r; return rc ? rc : fail(ABB_ERR_CUDA, "radix sort failed: %s", cudaGetErrorString(ce)); }
+    A.io.hops = o_hops.as<int32_t>(); A.io.rels = o_rels.as<int8_t>(); A.io.ncred = o_nc.as<int32_t>(); A.io.ntool = o_nt.as<int32_t>(); A.io.row_cap = count;
+    rank_gather_kernel<<<static_cast<unsigned>((count + 255) / 256), 256, 0, st>>>(A, RA, v2.as<uint32_t>(), first, count, o_rank.as<uint32_t>(), o_row.as<int64_t>());
+    g_launches++;
+    r->hops.resize(static_cast<size_t>(count) * 4); r->rels.resize(static_cast<size_t>(count) * 4); r->ncred.resize(count); r->ntool.resize(count);
+    r->risk_rank.resize(count); r->row.resize(count);
+    ce = cudaGetLastError();
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(r->hops.data(), o_hops.p, static_cast<size_t>(count) * 16, cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(r->rels.data(), o_rels.p, static_cast<size_t>(count) * 4, cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(r->ncred.data(), o_nc.p, static_cast<size_t>(count) * 4, cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(r->ntool.data(), o_nt.p, static_cast<size_t>(count) * 4, cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(r->risk_rank.data(), o_rank.p, static_cast<size_t>(count) * 4, cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(r->row.data(), o_row.p, static_cast<size_t>(count) * 8, cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    if (ce != cudaSuccess) { delete r; return fail(ABB_ERR_CUDA, "ranking failed: %s", cudaGetErrorString(ce)); }
+    *out = r;
+    return ABB_OK;
+}
+
 extern "C" int abb_exposure_host(abb_graph *g, const int32_t *findings, int64_t n_findings, int32_t max_depth, abb_walk_result **impact_out,
                                  abb_paths_result **paths_out) {
     if (!g || !impact_out || !paths_out || n_findings < 0 || (n_findings && !findings)) return fail(ABB_ERR_ARG, "bad arguments");

@@ -319,4 +319,76 @@ __global__ void __launch_bounds__(256) replicate_kernel(const PathsArgs A) {
     }
 }
 
+
+// ---- ranking (reference api/routes/graph.py:762-786): sort key of every row, then the requested page is gathered.
+// key (descending) = (risk rank, #hops, #distinct credential labels, #distinct tool labels); ties keep emission order
+// (Python's stable sort with reverse=True) — the radix sort below is stable on the complemented key.
+struct RankArgs {
+    const int32_t *base_id;       // [n_findings] index of the finding's base risk value
+    const uint32_t *risk_rank;    // [n_base * 5 * 15] dense rank of round(min(100, base + min(10, 3c) + min(10, .75t)), 2), c<=4, t<=14
+    const int32_t *ncu;           // [n_nodes] distinct credential labels of a server
+    const int32_t *ntu;           // [n_nodes] distinct tool labels of a server
+    unsigned long long *keys;     // [n_rows] complemented sort key
+    uint32_t *rows;               // [n_rows] row index
+};
+
+__device__ __forceinline__ unsigned long long rank_key(const PathsArgs &A, const RankArgs &R, int64_t fi, int64_t t, int32_t vs) {
+    const int4 tr = A.t_row[t];
+    const int nc = tr.z < 4 ? tr.z : 4, nt = tr.w < 14 ? tr.w : 14;
+    const unsigned long long rr = R.risk_rank[(static_cast<int64_t>(R.base_id[fi]) * 5 + nc) * 15 + nt];
+    const unsigned long long nh = (vs != tr.y) ? 4ull : 3ull;
+    const unsigned long long cu = static_cast<unsigned long long>(min(R.ncu[tr.y], 0x3FFFF)), tu = static_cast<unsigned long long>(min(R.ntu[tr.y], 0x3FFFF));
+    return ~((rr << 40) | (nh << 36) | (cu << 18) | tu);
+}
+
+__global__ void __launch_bounds__(256) rank_keys_kernel(const PathsArgs A, const RankArgs R) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    const int64_t nf = A.io.n_findings;
+    for (int64_t fb = warp * 32; fb < nf; fb += nwarps * 32) {
+        const int64_t fi = fb + lane;
+        int64_t l0 = 0, l1 = 0;
+        if (fi < nf) { l0 = A.link_off[fi]; l1 = A.link_off[fi + 1]; }
+        for (int64_t l = l0; l < l1; l++) {
+            const int64_t o0 = A.link_roff[l], rows = A.link_roff[l + 1] - o0;
+            if (rows > 8) continue;
+            const int32_t vs = A.link_vs[l]; const int64_t t0 = A.t_off_node[vs];
+            for (int64_t k = 0; k < rows; k++) { R.keys[o0 + k] = rank_key(A, R, fi, t0 + k, vs); R.rows[o0 + k] = static_cast<uint32_t>(o0 + k); }
+        }
+        for (int j = 0; j < 32; j++) {
+            const int64_t jl0 = __shfl_sync(FULL, l0, j), jl1 = __shfl_sync(FULL, l1, j);
+            const int64_t jfi = fb + j;
+            for (int64_t l = jl0; l < jl1; l++) {
+                const int64_t o0 = A.link_roff[l], rows = A.link_roff[l + 1] - o0;
+                if (rows <= 8) continue;
+                const int32_t vs = A.link_vs[l]; const int64_t t0 = A.t_off_node[vs];
+                for (int64_t k = lane; k < rows; k += 32) { R.keys[o0 + k] = rank_key(A, R, jfi, t0 + k, vs); R.rows[o0 + k] = static_cast<uint32_t>(o0 + k); }
+            }
+        }
+    }
+}
+
+// the page [first, first+count) of the sorted order -> flat rows (+ the risk rank so the host can print the float)
+__global__ void rank_gather_kernel(const PathsArgs A, const RankArgs R, const uint32_t *sorted_rows, int64_t first, int64_t count, uint32_t *out_rank,
+                                   int64_t *out_row) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const int64_t row = sorted_rows[first + i];
+    // finding = last f with f_off[f] <= row; link = last l in the finding with link_roff[l] <= row
+    int64_t lo = 0, hi = A.io.n_findings;
+    while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (A.io.f_off[mid] <= row) lo = mid; else hi = mid; }
+    const int64_t fi = lo;
+    int64_t a = A.link_off[fi], b = A.link_off[fi + 1];
+    while (b - a > 1) { const int64_t mid = (a + b) >> 1; if (A.link_roff[mid] <= row) a = mid; else b = mid; }
+    const int64_t l = a;
+    const int32_t vs = A.link_vs[l];
+    const int64_t t = A.t_off_node[vs] + (row - A.link_roff[l]);
+    emit_row(A, i, t, vs, A.io.findings[fi], A.link_rel[l]);
+    const int4 tr = A.t_row[t];
+    const int nc = tr.z < 4 ? tr.z : 4, nt = tr.w < 14 ? tr.w : 14;
+    out_rank[i] = R.risk_rank[(static_cast<int64_t>(R.base_id[fi]) * 5 + nc) * 15 + nt];
+    out_row[i] = row;
+}
+
 }  // namespace abb

@@ -290,6 +290,27 @@ class DeviceGraph:
             lib.abb_paths_result_free(pres)
         return w, p
 
+    def rank_exposure_paths(self, findings, base_id, risk_rank, ncu, ntu, offset: int = 0, limit: int = 100):
+        """Page [offset, offset+limit) of the exposure-path rows in the reference's ranking order; returns (PathRows-like, risk_rank, total)."""
+        lib = _lib.load()
+        f, b = _i32(findings), _i32(base_id)
+        table = np.ascontiguousarray(risk_rank, dtype=np.uint32)
+        cu, tu = _i32(ncu), _i32(ntu)
+        assert table.size % 75 == 0 and cu.shape[0] == self.n_nodes and tu.shape[0] == self.n_nodes and b.shape[0] == f.shape[0]
+        res = _vp()
+        _lib.check(lib.abb_paths_rank_host(self.handle, f.ctypes.data, int(f.shape[0]), b.ctypes.data, table.ctypes.data, table.size // 75, cu.ctypes.data,
+                                           tu.ctypes.data, int(offset), int(limit), C.byref(res)))
+        try:
+            k = int(lib.abb_rank_result_count(res))
+            rows = PathRows(
+                off=np.zeros(0, dtype=np.int64), hops=_view(lib.abb_rank_result_hops(res), k * 4, np.int32).reshape(k, 4),
+                rels=np.ascontiguousarray(_view(lib.abb_rank_result_rels(res), k * 4, np.int8).reshape(k, 4)[:, :3]),
+                ncred=_view(lib.abb_rank_result_ncred(res), k, np.int32), ntool=_view(lib.abb_rank_result_ntool(res), k, np.int32),
+            )
+            return rows, _view(lib.abb_rank_result_risk_rank(res), k, np.uint32), int(lib.abb_rank_result_total(res))
+        finally:
+            lib.abb_rank_result_free(res)
+
     # ── dependency reach ────────────────────────────────────────────────
     def dependency_reach(self, agents, rel_mask: int, vuln_pkg_mask: int) -> dict:
         lib = _lib.load()

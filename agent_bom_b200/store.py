@@ -24,7 +24,7 @@ from typing import Any
 
 from .graph.container import UnifiedGraph
 from .graph.dependency_reach import ReachabilityReport, compute_dependency_reach
-from .graph.exposure import derived_attack_paths, exposure_path_rows, materialize_attack_paths
+from .graph.exposure import derived_attack_paths, exposure_path_rows, materialize_attack_paths, ranked_attack_paths
 
 
 class B200UnsupportedOperationError(NotImplementedError):
@@ -121,8 +121,13 @@ class B200GraphStore:
         g = self._graph(tenant_id, scan_id)
         if g is None:
             return scan_id, "", [], 0
-        paths = sorted(self._paths(g), key=lambda p: (-p.composite_risk, p.source, p.target))
-        return g.scan_id, g.created_at, paths[offset: offset + limit], len(paths)
+        if g.attack_paths:     # materialised rows: the stores' order (api/graph_store.py:836-887 ORDER BY composite_risk DESC)
+            paths = sorted(g.attack_paths, key=lambda p: (-p.composite_risk, p.source, p.target))
+            return g.scan_id, g.created_at, paths[offset: offset + limit], len(paths)
+        # no materialised rows: the derived paths in their own ranking (api/routes/graph.py:1221-1230), ranked on the device —
+        # only the requested page becomes Python objects
+        page, total = ranked_attack_paths(g, offset, limit)
+        return g.scan_id, g.created_at, page, total
 
     # ── batched extensions ──────────────────────────────────────────────
     def impact_of_many(self, *, tenant_id: str = "", scan_id: str = "", node_ids: list[str], max_depth: int = 4) -> list[dict[str, Any] | None]:

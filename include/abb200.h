@@ -286,6 +286,25 @@ int64_t abb_paths_result_h2d_bytes(const abb_paths_result *r);
 int64_t abb_paths_result_d2h_bytes(const abb_paths_result *r);
 void abb_paths_result_free(abb_paths_result *r);
 
+/* Ranked page of exposure-path rows — the ordering of _derived_attack_paths (api/routes/graph.py:782-786): descending by
+ * (composite risk, #hops, #distinct credential labels, #distinct tool labels), ties in emission order.  The float
+ * formula (:762-771, Python round) stays on the host: the caller passes, per finding, the index of its base risk
+ * value, and a table risk_rank[n_base][5][15] with the dense rank of the rounded score for each (base, min(ncred,4),
+ * min(ntool,14)); ncu / ntu are the per-server counts of distinct credential / tool labels.  Returns rows
+ * [offset, offset+limit) of the sorted order plus the total row count. */
+typedef struct abb_rank_result abb_rank_result;
+int abb_paths_rank_host(abb_graph *g, const int32_t *findings, int64_t n_findings, const int32_t *base_id, const uint32_t *risk_rank,
+                        int64_t n_base, const int32_t *ncu, const int32_t *ntu, int64_t offset, int64_t limit, abb_rank_result **out);
+int64_t abb_rank_result_total(const abb_rank_result *r);
+int64_t abb_rank_result_count(const abb_rank_result *r);
+const int32_t *abb_rank_result_hops(const abb_rank_result *r);       /* [count*4] */
+const int8_t *abb_rank_result_rels(const abb_rank_result *r);        /* [count*4] */
+const int32_t *abb_rank_result_ncred(const abb_rank_result *r);
+const int32_t *abb_rank_result_ntool(const abb_rank_result *r);
+const uint32_t *abb_rank_result_risk_rank(const abb_rank_result *r); /* [count] index into the caller's sorted score list */
+const int64_t *abb_rank_result_row(const abb_rank_result *r);        /* [count] emission-order row index */
+void abb_rank_result_free(abb_rank_result *r);
+
 /* ------------------------------------------------------------------------
  * One "exposure traversal" per finding = impact_of(f, max_depth) + f's derived
  * exposure paths (the unit of BASELINE.json's metric).  Host-buffer form used

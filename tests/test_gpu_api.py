@@ -111,6 +111,27 @@ def test_derived_attack_paths(name):
         assert a.credential_exposure == b["creds"] and a.tool_exposure == b["tools"] and a.vuln_ids == b["vuln_ids"]
 
 
+@pytest.mark.parametrize("name", ALL_FIXTURES)
+def test_ranked_attack_paths_pages(name):
+    """Device-side ranking: every page equals the corresponding slice of the reference's sorted AttackPath list."""
+    from agent_bom_b200.graph import ranked_attack_paths
+    from agent_bom_b200.graph.schema import REL_CODE
+
+    doc, g = load(name), graph(name)
+    ids = doc["node_ids"]
+    want = doc["cases"]["derived_paths"]
+    total_want = len(want)
+    for offset, limit in ((0, total_want + 5), (0, 7), (3, 11), (max(0, total_want - 4), 10), (total_want + 3, 5)):
+        got, total = ranked_attack_paths(g, offset, limit)
+        assert total == total_want
+        ref = want[offset: offset + limit]
+        assert len(got) == len(ref)
+        for a, b in zip(got, ref):
+            assert (a.source, a.target, a.hops) == (ids[b["source"]], ids[b["target"]], [ids[h] for h in b["hops"]])
+            assert [REL_CODE[e] for e in a.edges] == b["edges"] and a.composite_risk == b["risk"]
+            assert a.credential_exposure == b["creds"] and a.tool_exposure == b["tools"]
+
+
 def test_store_drop_in():
     """GraphStoreProtocol traversal subset on the GPU: same answers as the engine-level calls; None / [] conventions."""
     from agent_bom_b200.store import B200GraphStore
@@ -130,6 +151,8 @@ def test_store_drop_in():
     sid, created, page, total = store.attack_paths(tenant_id="t", limit=2)
     assert sid == "golden" and total == len(doc["cases"]["derived_paths"]) and len(page) == 2
     assert page[0].composite_risk >= page[1].composite_risk
+    want = doc["cases"]["derived_paths"]
+    assert [p.hops for p in page] == [[doc["node_ids"][h] for h in w["hops"]] for w in want[:2]]
     only = store.attack_paths_for_sources(tenant_id="t", source_ids={"user:u"})
     assert only and all(p.source == "user:u" for p in only)
     many = store.impact_of_many(tenant_id="t", node_ids=["vuln:cve", "nope", "mis:m"])
