@@ -137,3 +137,41 @@ def test_oracle_replay_of_a_sample(scale):
     np.testing.assert_array_equal(got_p.rels, want_p.rels)
     np.testing.assert_array_equal(got_p.ncred, want_p.ncred)
     np.testing.assert_array_equal(got_p.ntool, want_p.ntool)
+
+
+def test_ranked_pages_match_a_host_sort(scale):
+    """Device ranking of every exposure-path row vs a numpy stable sort of the expanded rows (api/routes/graph.py:782-786 order)."""
+    est, host, dg, og = scale
+    stride = 8 if len(est.findings) > 2_000_000 else 1
+    f = np.ascontiguousarray(est.findings[::stride])
+    rows = dg.exposure_paths_many(f)
+    n_rows = rows.hops.shape[0]
+    # base risk of a finding = severity rank * 20 (risk_score is 0 in the estates): critical 100, high 80, medium 60, low 40
+    base_of_sev = np.asarray([100.0, 80.0, 60.0, 40.0])
+    base = base_of_sev[est.node_sev[f]]
+    base_vals, base_id = np.unique(base, return_inverse=True)
+    scores = np.empty((len(base_vals), 5, 15))
+    for bi, b in enumerate(base_vals.tolist()):
+        for nc in range(5):
+            for nt in range(15):
+                risk = b
+                risk += min(10.0, nc * 3.0)
+                risk += min(10.0, nt * 0.75)
+                scores[bi, nc, nt] = round(min(100.0, risk), 2)
+    levels = np.unique(scores)
+    table = np.searchsorted(levels, scores).astype(np.uint32)
+    # labels are unique per node in the estates, so distinct-label counts == edge counts of the server
+    ncu = np.zeros(host.n_nodes, dtype=np.int32); ntu = np.zeros(host.n_nodes, dtype=np.int32)
+    ncu[rows.hops[:, 1]] = rows.ncred; ntu[rows.hops[:, 1]] = rows.ntool
+    per_finding = np.diff(rows.off)
+    row_base = np.repeat(base_id, per_finding)
+    risk = scores[row_base, np.minimum(rows.ncred, 4), np.minimum(rows.ntool, 14)]
+    nh = np.where(rows.hops[:, 2] >= 0, 4, 3)
+    order = np.lexsort((np.arange(n_rows), -ntu[rows.hops[:, 1]], -ncu[rows.hops[:, 1]], -nh, -risk))
+    for offset, limit in ((0, 20000), (n_rows // 2, 5000), (max(0, n_rows - 3000), 5000)):
+        page, rank, total = dg.rank_exposure_paths(f, base_id.astype(np.int32), table, ncu, ntu, offset, limit)
+        assert total == n_rows
+        want = order[offset: offset + limit]
+        np.testing.assert_array_equal(page.hops, rows.hops[want])
+        np.testing.assert_array_equal(page.rels, rows.rels[want])
+        np.testing.assert_array_equal(levels[rank], risk[want])
