@@ -186,6 +186,8 @@ struct abb_graph {
     DevBuf dd_sig, dd_ssig, dd_q, dd_sq, dd_head, dd_gid, dd_hp, dd_glen, dd_goff, dd_arena, dd_memoff, dd_memsrc, dd_memstate, dd_indiv, dd_cnt, dd_tmp;
     DevBuf dd_gstart, dd_gcount, dd_gmaxd, dd_gflags, dd_ghist;
     bool dedup_enabled = true;
+    int slice_align = 0;        // set while a host-mapped arena is the walk target
+    bool align_direct = true;
     bool zero_copy = true;      // host-API walks write the node arena straight into pinned host memory when its size is known
     int64_t last_walk_queries = 0;
     bool last_walk_dedup = false;
@@ -253,6 +255,7 @@ static int graph_finish_init(abb_graph *g) {
     if (const char *e = getenv("ABB_DEDUP")) g->dedup_enabled = atoi(e) != 0;
     if (const char *e = getenv("ABB_S1_CFG")) g->s1_cfg = atoi(e);
     if (const char *e = getenv("ABB_ZEROCOPY")) g->zero_copy = atoi(e) != 0;
+    if (const char *e = getenv("ABB_ALIGN_DIRECT")) g->align_direct = atoi(e) != 0;
     if (!g->v.rank) {
         if (int rc = g->identity_rank.ensure(static_cast<size_t>(n + 1) * 4)) return rc;
         std::vector<int32_t> id(static_cast<size_t>(n));
@@ -474,6 +477,7 @@ static int enqueue_tiers(abb_graph *g, WalkArgs A, int64_t max_items, unsigned l
     const bool meta = A.spec.rel_mask != 0xFFFFFFFFu || (fl & ABB_WALK_TRAVERSABLE_ONLY);
     const bool bud = A.spec.max_nodes >= 0 || A.spec.max_edges >= 0;
     A.ctl = ctl; A.overflow = ov1;
+    A.slice_align = g->slice_align;
     if (g->s1_cfg == 1) { if (int rc = launch_smem_variant<512, 256, 8>(g, A, max_items, par, meta, bud, st)) return rc; }
     else if (int rc = launch_smem_variant<S1_H, S1_Q, S1_WARPS>(g, A, max_items, par, meta, bud, st)) return rc;
     A.qlist = ov1; A.nq = 0; A.nq_dev = ctl + 1; A.ctl = ctl + 4; A.overflow = ov2;
@@ -683,7 +687,7 @@ extern "C" int64_t abb_walk_result_d2h_bytes(const abb_walk_result *r) { return 
 // straight into that pinned host block (UVA), so the PCIe transfer of the largest output overlaps the traversal
 // instead of following it; if the estimate turns out too small the walk is re-run into a device arena.
 static int walk_device_stage(abb_graph *g, const abb_walk_spec *spec, const int32_t *roots, const int64_t *root_off, const int32_t *targets,
-                             int64_t nq, abb_walk_io *io_out, unsigned long long totals[2], int64_t *h2d, HostBlock *direct_nodes = nullptr) {
+                             int64_t nq, abb_walk_io *io_out, unsigned long long totals[3], int64_t *h2d, HostBlock *direct_nodes = nullptr) {
     cudaStream_t st = g->stream;
     const uint32_t fl = spec->flags;
     const int64_t n_roots = root_off ? root_off[nq] : nq;
@@ -698,7 +702,7 @@ static int walk_device_stage(abb_graph *g, const abb_walk_spec *spec, const int3
     if (int rc = g->d_qflags.ensure(q1 * 4)) return rc;
     if (fl & ABB_WALK_EDGES) { if (int rc = g->d_qestart.ensure(q1 * 8)) return rc; if (int rc = g->d_qecount.ensure(q1 * 8)) return rc; }
     if (fl & ABB_WALK_HIST) if (int rc = g->d_qhist.ensure(q1 * ABB_N_ENTITY_TYPES * 4)) return rc;
-    if (int rc = g->d_totals.ensure(2 * sizeof(unsigned long long))) return rc;
+    if (int rc = g->d_totals.ensure(3 * sizeof(unsigned long long))) return rc;
     *h2d = 0;
     if (n_roots) { CUDA_TRY(cudaMemcpyAsync(g->d_roots.p, roots, static_cast<size_t>(n_roots) * 4, cudaMemcpyHostToDevice, st)); *h2d += n_roots * 4; }
     if (root_off) { CUDA_TRY(cudaMemcpyAsync(g->d_root_off.p, root_off, q1 * 8, cudaMemcpyHostToDevice, st)); *h2d += static_cast<int64_t>(q1) * 8; }
@@ -709,7 +713,7 @@ static int walk_device_stage(abb_graph *g, const abb_walk_spec *spec, const int3
     bool direct = direct_nodes && g->zero_copy && g->hint_nodes > 0 && !(fl & (ABB_WALK_PARENTS | ABB_WALK_DEPTHS | ABB_WALK_EDGES));
     if (direct) {
         // same batch size as last time: its exact need plus a little; otherwise scale the last per-query average generously
-        node_cap = (nq == g->hint_nq) ? g->hint_last_nodes + g->hint_last_nodes / 64 + 4096
+        node_cap = (nq == g->hint_nq) ? g->hint_last_nodes + g->hint_last_nodes / 64 + 4096 + (g->align_direct ? 32 * nq : 0)
                                       : static_cast<int64_t>(1.5 * static_cast<double>(g->hint_last_nodes) / std::max<int64_t>(g->hint_nq, 1) * nq) + 4096;
         direct = direct_nodes->alloc(static_cast<size_t>(node_cap) * 4);
     }
@@ -727,10 +731,14 @@ static int walk_device_stage(abb_graph *g, const abb_walk_spec *spec, const int3
         io.parent = g->d_parent.as<int32_t>(); io.depth = g->d_depth.as<int32_t>(); io.node_cap = node_cap;
         io.edges = g->d_edges.as<uint32_t>(); io.edge_cap = edge_cap; io.totals = g->d_totals.as<unsigned long long>();
         CUDA_TRY(cudaEventRecord(g->ev[0], st));
-        if (int rc = enqueue_walk(g, spec, &io, st)) return rc;
+        g->slice_align = (direct && g->align_direct) ? 32 : 0;
+        CUDA_TRY(cudaMemsetAsync(g->d_totals.as<unsigned long long>() + 2, 0, sizeof(unsigned long long), st));
+        int erc = enqueue_walk(g, spec, &io, st);
+        g->slice_align = 0;
+        if (erc) return erc;
         CUDA_TRY(cudaEventRecord(g->ev[1], st));
         g->walk_timed = true;
-        CUDA_TRY(cudaMemcpyAsync(totals, g->d_totals.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(totals, g->d_totals.p, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
         unsigned long long fatal = 0, fatal2 = 0;
         CUDA_TRY(cudaMemcpy(&fatal, g->ctl.as<unsigned long long>() + 10, sizeof fatal, cudaMemcpyDeviceToHost));
@@ -751,7 +759,7 @@ static int walk_device_stage(abb_graph *g, const abb_walk_spec *spec, const int3
 
 // sync == false: the copies go to the graph's copy stream (ordered after everything enqueued so far on the main stream)
 // so that kernels enqueued next on the main stream overlap them; the caller synchronises the copy stream.
-static int walk_collect(abb_graph *g, const abb_walk_spec *spec, const abb_walk_io &io, const unsigned long long totals[2], int64_t h2d,
+static int walk_collect(abb_graph *g, const abb_walk_spec *spec, const abb_walk_io &io, const unsigned long long totals[3], int64_t h2d,
                         abb_walk_result **out, bool sync, HostBlock *direct_nodes = nullptr) {
     cudaStream_t st = g->stream;
     if (!sync) {
@@ -780,7 +788,7 @@ static int walk_collect(abb_graph *g, const abb_walk_spec *spec, const abb_walk_
     cudaError_t e = cudaSuccess;
     auto acc = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
     acc(d2h(r->q_start, io.q_start, q * 8)); acc(d2h(r->q_count, io.q_count, q * 4)); acc(d2h(r->q_maxd, io.q_maxd, q * 4)); acc(d2h(r->q_flags, io.q_flags, q * 4));
-    if (have_nodes) r->d2h += static_cast<int64_t>(tn * 4); else acc(d2h(r->nodes, io.nodes, tn * 4));
+    if (have_nodes) r->d2h += static_cast<int64_t>((totals[2] ? totals[2] : static_cast<unsigned long long>(tn)) * 4); else acc(d2h(r->nodes, io.nodes, tn * 4));
     if (fl & ABB_WALK_EDGES) { acc(d2h(r->q_estart, io.q_estart, q * 8)); acc(d2h(r->q_ecount, io.q_ecount, q * 8)); acc(d2h(r->edges, io.edges, te * 4)); }
     if (fl & ABB_WALK_HIST) acc(d2h(r->q_hist, io.q_hist, q * ABB_N_ENTITY_TYPES * 4));
     if (fl & ABB_WALK_PARENTS) acc(d2h(r->parent, io.parent, tn * 4));
@@ -797,7 +805,7 @@ extern "C" int abb_walk_host(abb_graph *g, const abb_walk_spec *spec, const int3
     if ((spec->flags & ABB_WALK_TARGET) && !targets) return fail(ABB_ERR_ARG, "TARGET needs targets");
     DeviceGuard dg(g->device);
     std::lock_guard<std::mutex> lk(g->mu);
-    abb_walk_io io{}; unsigned long long totals[2] = {0, 0}; int64_t h2d = 0;
+    abb_walk_io io{}; unsigned long long totals[3] = {0, 0, 0}; int64_t h2d = 0;
     HostBlock direct;
     if (int rc = walk_device_stage(g, spec, roots, root_off, targets, n_queries, &io, totals, &h2d, &direct)) { direct.release(); return rc; }
     int rc = walk_collect(g, spec, io, totals, h2d, out, true, &direct);
@@ -1165,7 +1173,7 @@ extern "C" int abb_exposure_host(abb_graph *g, const int32_t *findings, int64_t 
     auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
     const auto t0 = now();
     abb_walk_spec spec = abb_spec_impact_of(max_depth);
-    abb_walk_io io{}; unsigned long long totals[2] = {0, 0}; int64_t h2d = 0;
+    abb_walk_io io{}; unsigned long long totals[3] = {0, 0, 0}; int64_t h2d = 0;
     HostBlock direct;
     if (int rc = walk_device_stage(g, &spec, findings, nullptr, nullptr, n_findings, &io, totals, &h2d, &direct)) { direct.release(); return rc; }
     const auto t1 = now();

@@ -52,6 +52,7 @@ struct WalkArgs {
     int64_t g_words, g_qcap;
     // canonical (root-frontier de-duplicated) mode: a query is a GROUP of sources that share their level-1 frontier,
     // seeded with that frontier; depths are offset by one and every member source is tested against the visited set
+    int32_t slice_align;         // result slices start on a multiple of this many ints (32 when the arena is host-mapped: whole 128-byte lines per PCIe write)
     int32_t depth_bias;          // added to emitted depths / max depth (1 in canonical mode)
     int32_t hist_roots;          // count the seeded roots in the histogram too
     const int64_t *mem_off;      // [groups+1] member range of each group in the sorted member arrays (NULL = not canonical)
@@ -404,9 +405,14 @@ __device__ bool walk_one(const WalkArgs &A, Store &st, int64_t q, int lane, uint
         }
     }
     unsigned long long start = 0;
-    if (lane == 0) start = atomicAdd(io.totals, static_cast<unsigned long long>(count));
+    const unsigned long long reserve = A.slice_align > 1 ? ((static_cast<unsigned long long>(count) + A.slice_align - 1) / A.slice_align) * A.slice_align
+                                                         : static_cast<unsigned long long>(count);
+    if (lane == 0) {
+        start = atomicAdd(io.totals, reserve);
+        if (A.slice_align > 1) atomicAdd(io.totals + 2, static_cast<unsigned long long>(count));   // ints really written (host path only: totals has 3 slots there)
+    }
     start = __shfl_sync(FULL, start, 0);
-    const bool fits = static_cast<long long>(start) + count <= io.node_cap;
+    const bool fits = static_cast<long long>(start + reserve) <= io.node_cap;
     if ((fl & ABB_WALK_HIST) && lane < ABB_N_ENTITY_TYPES) hist_bins[lane] = 0;
     __syncwarp();
     if (fits || (fl & ABB_WALK_HIST)) {
