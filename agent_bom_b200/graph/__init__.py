@@ -11,10 +11,11 @@ from .container import UnifiedGraph
 from .dependency_reach import PackageReachability, ReachabilityReport, VulnerabilityReachability, compute_dependency_reach
 from .exposure import derived_attack_paths, exposure_path_rows, materialize_attack_paths, node_risk_100, ranked_attack_paths
 from .model import AttackPath, UnifiedEdge, UnifiedNode
+from .snapshot import SnapshotGraph, load_snapshot
 from .schema import FINDING_ENTITY_TYPES, SEVERITY_RANK, EntityType, NodeStatus, RelationshipType
 
 __all__ = [
-    "AttackPath", "EntityType", "FINDING_ENTITY_TYPES", "NodeStatus", "PackageReachability", "ReachabilityReport", "RelationshipType", "SEVERITY_RANK",
+    "AttackPath", "EntityType", "FINDING_ENTITY_TYPES", "NodeStatus", "PackageReachability", "ReachabilityReport", "RelationshipType", "SEVERITY_RANK", "SnapshotGraph", "load_snapshot",
     "UnifiedEdge", "UnifiedGraph", "UnifiedNode", "VulnerabilityReachability", "build_unified_graph_from_report", "compute_dependency_reach", "derived_attack_paths", "exposure_path_rows",
     "materialize_attack_paths", "node_risk_100", "ranked_attack_paths",
 ]

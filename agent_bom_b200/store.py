@@ -67,14 +67,31 @@ class B200GraphStore:
                 return g
         if self._inner is None:
             return None
-        loaded = self._inner.load_graph(tenant_id=tenant_id, scan_id=scan_id)
-        if loaded is None or not getattr(loaded, "nodes", None):
-            return None
-        g = UnifiedGraph.from_graph(loaded, device=self._device)
+        g = self._load_topology_first(tenant_id, scan_id)
+        if g is None:
+            loaded = self._inner.load_graph(tenant_id=tenant_id, scan_id=scan_id)
+            if loaded is None or not getattr(loaded, "nodes", None):
+                return None
+            g = UnifiedGraph.from_graph(loaded, device=self._device)
         with self._lock:
             self._graphs[(tenant_id or "", g.scan_id or scan_id)] = g
             self._latest.setdefault(tenant_id or "", g.scan_id or scan_id)
         return g
+
+    def _load_topology_first(self, tenant_id: str, scan_id: str) -> UnifiedGraph | None:
+        """Cache miss over a SQLite-backed inner store (reference api/graph_store.py:259-263 keeps ``_db_path``): scan the
+        topology columns only (graph/snapshot.py) instead of materialising every node / edge record."""
+        db_path = getattr(self._inner, "_db_path", None)
+        if db_path is None:
+            return None
+        from pathlib import Path
+
+        from .graph.snapshot import load_snapshot
+
+        if not Path(db_path).exists():
+            return None
+        g = load_snapshot(db_path, tenant_id=tenant_id, scan_id=scan_id, device=self._device)
+        return g if g.nodes else None
 
     def load_graph(self, *, tenant_id: str = "", scan_id: str = "", entity_types: set[str] | None = None, min_severity_rank: int = 0):
         if (entity_types or min_severity_rank) and self._inner is not None:

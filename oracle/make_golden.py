@@ -404,13 +404,77 @@ def builder_identity():
     print(f"-> {path} {path.stat().st_size / 1024:.0f} KiB")
 
 
+def snapshot_identity():
+    """Pin agent_bom_b200.graph.snapshot.load_snapshot: a SQLite file written by the reference's own save_graph, and what the
+    reference's load_graph makes of every (tenant, scan) in it — node order, edge order, records, materialised paths."""
+    import sqlite3
+    import tempfile
+
+    from agent_bom.db import graph_store as ref_db
+
+    out_dir = OUT / "snapshot"
+    out_dir.mkdir(parents=True, exist_ok=True)
+    tmp = Path(tempfile.mkdtemp()) / "graph.sqlite"
+    conn = sqlite3.connect(str(tmp))
+    conn.row_factory = sqlite3.Row
+    ref_db._init_db(conn)
+
+    def stamped(g, scan, tenant, created):
+        g.scan_id, g.tenant_id, g.created_at = scan, tenant, created
+        return g
+
+    mesh = stamped(mesh_inventory(), "scan-a", "default", "2026-01-01T00:00:00+00:00")
+    ref_db.save_graph(conn, mesh)
+    dense = stamped(estate(12, dense=(4, 8, 2)), "scan-b", "default", "2026-02-01T00:00:00+00:00")
+    dense.attack_paths = _derived_attack_paths(dense)[:40]          # materialised rows win over derived ones
+    ref_db.save_graph(conn, dense)
+    # scan-a saved again with one node and its edges gone and the rest re-inserted: INSERT OR REPLACE moves the surviving rows
+    mesh2 = stamped(mesh_inventory(), "scan-a", "default", "2026-01-01T00:00:00+00:00")
+    victim = next(nid for nid, n in mesh2.nodes.items() if enum_value(n.entity_type) == "package")
+    del mesh2.nodes[victim]
+    ref_db.save_graph(conn, mesh2)
+    probe = stamped(kat_probe(), "scan-a", "acme", "2026-03-01T00:00:00+00:00")
+    ref_db.save_graph(conn, probe)
+    blank = stamped(kat_derived(), "scan-z", "", "2026-04-01T00:00:00+00:00")   # blank tenant -> "default", becomes the newest there
+    ref_db.save_graph(conn, blank)
+    conn.commit()
+
+    cases = []
+    for tenant, scan in (("default", "scan-a"), ("default", "scan-b"), ("default", ""), ("", "scan-z"), ("acme", ""), ("acme", "scan-a"), ("acme", "missing"), ("nobody", "")):
+        g = ref_db.load_graph(conn, tenant_id=tenant, scan_id=scan)
+        nodes = list(g.nodes.values())
+        sample_nodes = nodes[:: max(1, len(nodes) // 12)]
+        sample_edges = g.edges[:: max(1, len(g.edges) // 12)]
+        cases.append({
+            "tenant": tenant, "scan": scan, "scan_id": g.scan_id, "tenant_id": g.tenant_id, "created_at": g.created_at if g.scan_id else "",
+            "nodes": [[n.id, enum_value(n.entity_type), n.label, n.severity, float(n.risk_score or 0.0)] for n in nodes],
+            "edges": [[e.source, e.target, enum_value(e.relationship), e.direction, bool(e.traversable), float(e.weight)] for e in g.edges],
+            "attack_paths": [p.to_dict() for p in g.attack_paths],
+            "interaction_risks": [r.to_dict() for r in g.interaction_risks],
+            "node_dicts": [n.to_dict() for n in sample_nodes],
+            "edge_dicts": [e.to_dict() for e in sample_edges],
+        })
+        print(f"snapshot_identity {tenant!r}/{scan!r}: -> {g.scan_id!r} {len(g.nodes)} nodes {len(g.edges)} edges {len(g.attack_paths)} paths")
+    conn.close()
+    with gzip.GzipFile(out_dir / "graph.sqlite.gz", "wb", mtime=0) as fh:
+        fh.write(tmp.read_bytes())
+    with gzip.GzipFile(out_dir / "expected.json.gz", "wb", mtime=0) as fh:
+        fh.write(json.dumps(cases, separators=(",", ":"), sort_keys=True, default=str).encode())
+    print(f"-> {out_dir} {sum(f.stat().st_size for f in out_dir.iterdir()) / 1024:.0f} KiB")
+
+
 def main():
+    if "--snapshot-only" in sys.argv:
+        snapshot_identity()
+        return
     if "--identity-only" in sys.argv:
         estate_identity()
         builder_identity()
+        snapshot_identity()
         return
     estate_identity()
     builder_identity()
+    snapshot_identity()
     rng = random.Random(20260921)
     run_battery("kat_schema", kat_schema(), rng, small=True)
     run_battery("kat_directed", kat_directed(), rng, small=True)

@@ -185,3 +185,76 @@ def test_mutation_invalidates_device_cache():
     g.add_edge(UnifiedEdge(source="s", target="v", relationship=RelationshipType.VULNERABLE_TO))
     assert g.impact_of("v")["affected_nodes"] == ["a", "s"]
     assert g.reachable_from("v") == {"v"}                                                    # tests/test_graph_schema.py:926-946
+
+
+@pytest.mark.parametrize("tenant,scan", [("default", "scan-a"), ("default", "scan-b"), ("acme", "")])
+def test_snapshot_graph_answers_like_a_record_graph(tmp_path, tenant, scan):
+    """A topology-first snapshot (graph/snapshot.py, thin lazy records) gives the answers of a graph made of full records with the
+    reference's load_graph content (tests/golden/snapshot, written and read back by the reference), and of the CPU oracle."""
+    import gzip
+    import json
+    from pathlib import Path
+
+    import numpy as np
+
+    from agent_bom_b200.graph import EntityType, RelationshipType, UnifiedEdge, UnifiedGraph, UnifiedNode
+    from agent_bom_b200.graph.exposure import derived_attack_paths, ranked_attack_paths
+    from agent_bom_b200.graph.schema import ENTITY_CODE, REL_CODE
+    from agent_bom_b200.graph.snapshot import load_snapshot
+    from agent_bom_b200.store import B200GraphStore
+    from oracle import oracle as orc
+
+    gold = Path(__file__).parent / "golden" / "snapshot"
+    db = tmp_path / "graph.sqlite"
+    db.write_bytes(gzip.decompress((gold / "graph.sqlite.gz").read_bytes()))
+    case = next(c for c in json.loads(gzip.decompress((gold / "expected.json.gz").read_bytes())) if c["tenant"] == tenant and c["scan"] == scan)
+    snap = load_snapshot(db, tenant_id=tenant, scan_id=scan)
+    rec = UnifiedGraph(scan_id=case["scan_id"], tenant_id=case["tenant_id"], created_at=case["created_at"])
+    for nid, kind, label, sev, risk in case["nodes"]:
+        rec.add_node(UnifiedNode(id=nid, entity_type=EntityType(kind), label=label, severity=sev, risk_score=risk))
+    for s, t, r, direction, trav, w in case["edges"]:
+        rec.add_edge(UnifiedEdge(source=s, target=t, relationship=RelationshipType(r), direction=direction, traversable=trav, weight=w))
+    ids = [n[0] for n in case["nodes"]]
+    assert snap.impact_of_many(ids, 4) == rec.impact_of_many(ids, 4)
+    some = ids[:: max(1, len(ids) // 40)]
+    assert snap.bfs_many(some, 4, True) == rec.bfs_many(some, 4, True)
+    assert snap.bfs_many(some, 3, False) == rec.bfs_many(some, 3, False)
+    # the oracle on the same arrays (parity anchor, not just self-consistency)
+    idx = {nid: i for i, nid in enumerate(ids)}
+    og = orc.build_csr(len(ids), np.asarray([idx[e[0]] for e in case["edges"]], np.int32), np.asarray([idx[e[1]] for e in case["edges"]], np.int32),
+                       np.asarray([REL_CODE[e[2]] for e in case["edges"]], np.uint8),
+                       np.asarray([(1 if e[4] else 0) | (2 if e[3] == "bidirectional" else 0) for e in case["edges"]], np.uint8),
+                       np.asarray([ENTITY_CODE[n[1]] for n in case["nodes"]], np.uint8))
+    want = orc.impact_many(og, np.arange(len(ids), dtype=np.int32), 4)
+    got = snap.impact_of_many(ids, 4)
+    for q in range(len(ids)):
+        a, b = int(want.off[q]), int(want.off[q + 1])
+        assert got[q]["affected_nodes"] == sorted(ids[i] for i in want.nodes[a:b].tolist()) and got[q]["max_depth_reached"] == int(want.maxd[q])
+    for direction in ("forward", "reverse", "both"):
+        for roots in (some[:1], some[1:4]):
+            a_sub, a_depth, a_tr = snap.traverse_subgraph(roots, direction=direction, max_depth=3, max_nodes=60, max_edges=200)
+            b_sub, b_depth, b_tr = rec.traverse_subgraph(roots, direction=direction, max_depth=3, max_nodes=60, max_edges=200)
+            assert (sorted(a_sub.nodes), a_depth, a_tr) == (sorted(b_sub.nodes), b_depth, b_tr)
+            assert [(e.source, e.target, e.relationship, e.direction, e.traversable) for e in a_sub.edges] == \
+                   [(e.source, e.target, e.relationship, e.direction, e.traversable) for e in b_sub.edges]
+            assert all(n._full is not None for n in a_sub.nodes.values())           # hydrated in bulk, ready for to_dict()
+            assert all(e.to_dict()["id"] == e.id for e in a_sub.edges)
+    snap_paths, rec_paths = derived_attack_paths(snap), derived_attack_paths(rec)
+    if case["attack_paths"]:
+        assert [p.to_dict() for p in snap_paths] == case["attack_paths"]          # materialised rows win
+    else:
+        assert [p.to_dict() for p in snap_paths] == [p.to_dict() for p in rec_paths]
+        page, total = ranked_attack_paths(snap, 0, 25)
+        assert total == len(rec_paths) and [p.to_dict() for p in page] == [p.to_dict() for p in rec_paths[:25]]
+
+    class Inner:
+        _db_path = db
+
+        def load_graph(self, **_kw):
+            raise AssertionError("the topology-first path should have served this")
+
+    store = B200GraphStore(inner=Inner())
+    probe = ids[len(ids) // 2]
+    assert store.impact_of(tenant_id=tenant, scan_id=scan, node_id=probe) == rec.impact_of(probe)
+    paths, reach = store.bfs_paths(tenant_id=tenant, scan_id=scan, source=some[0], max_depth=4)
+    assert paths == rec.bfs(some[0], 4, True)
