@@ -22,6 +22,7 @@
 #include "dedup.cuh"
 #include "paths.cuh"
 #include "reach.cuh"
+#include "union.cuh"
 #include "walk.cuh"
 
 using namespace abb;
@@ -1194,3 +1195,4 @@ extern "C" int abb_exposure_host(abb_graph *g, const int32_t *findings, int64_t 
 }
 
 #include "reach_host.inl"
+#include "union_host.inl"

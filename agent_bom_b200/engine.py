@@ -347,3 +347,32 @@ class DeviceGraph:
 
     def last_paths_ms(self) -> float:
         return float(_lib.load().abb_last_paths_ms(self.handle))
+
+
+def group_union(member_off, members, item_off, items, w0=None, w1=None, *, device: int = 0):
+    """Per group: sorted de-duplicated union of its members' item lists and the maxima of two per-member byte weights
+    (``abb_group_union_host``; the device reduction behind effective-reach scoring).  Returns ``(off, items, w0max, w1max, ms)``."""
+    lib = _lib.load()
+    moff = np.ascontiguousarray(member_off, dtype=np.int64)
+    mem = _i32(members)
+    ioff = np.ascontiguousarray(item_off, dtype=np.int64)
+    it = _i32(items)
+    n_groups, n_members = int(moff.shape[0]) - 1, int(ioff.shape[0]) - 1
+    if n_groups < 0 or n_members < 0:
+        raise ValueError("offset arrays need at least one entry")
+    a0 = np.ascontiguousarray(w0, dtype=np.uint8) if w0 is not None else None
+    a1 = np.ascontiguousarray(w1, dtype=np.uint8) if w1 is not None else None
+    for w in (a0, a1):
+        if w is not None and int(w.shape[0]) != n_members:
+            raise ValueError("weights must have one byte per member")
+    res = _vp()
+    _lib.check(lib.abb_group_union_host(device, n_groups, moff.ctypes.data, mem.ctypes.data, n_members, ioff.ctypes.data, it.ctypes.data,
+                                        a0.ctypes.data if a0 is not None else None, a1.ctypes.data if a1 is not None else None, C.byref(res)))
+    try:
+        off = _view(lib.abb_union_result_off(res), n_groups + 1, np.int64).copy()
+        out = _view(lib.abb_union_result_items(res), int(off[-1]), np.int32).copy()
+        g0 = _view(lib.abb_union_result_w0(res), n_groups, np.uint8).copy()
+        g1 = _view(lib.abb_union_result_w1(res), n_groups, np.uint8).copy()
+        return off, out, g0, g1, float(lib.abb_union_result_ms(res))
+    finally:
+        lib.abb_union_result_free(res)

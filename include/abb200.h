@@ -340,6 +340,26 @@ const int32_t *abb_reach_vuln_agents(const abb_reach_result *r); /* sorted by no
 const int32_t *abb_reach_vuln_minhop(const abb_reach_result *r);
 void abb_reach_result_free(abb_reach_result *r);
 
+/* ---- per-group union of member item lists (effective-reach scoring) ------------------------------------------
+ * Replaces the per-vulnerability reduction of agent_bom/effective_reach.py:372-426 (`compute`): for every group
+ * (a vulnerability) over its members (the servers VULNERABLE_TO it, effective_reach.py:265-279) return
+ *   - the sorted, de-duplicated union of the members' item lists (label ranks of reachable tools / credentials /
+ *     agents, :281-353 — the caller encodes the category in the top bits of the item so one call serves all three),
+ *   - the maximum of two per-member byte weights (strongest tool capability / credential tier, :389-398).
+ * member_off[n_groups+1] / members[]: CSR of member indices per group; item_off[n_members+1] / items[]: CSR of
+ * non-negative int32 items per member; w0 / w1: [n_members] or NULL.  All pointers are host memory.
+ * Result: off[n_groups+1], items[off[n_groups]] ascending within a group, w0[n_groups], w1[n_groups]. */
+typedef struct abb_union_result abb_union_result;
+int abb_group_union_host(int device, int64_t n_groups, const int64_t *member_off, const int32_t *members, int64_t n_members,
+                         const int64_t *item_off, const int32_t *items, const uint8_t *w0, const uint8_t *w1,
+                         abb_union_result **out);
+const int64_t *abb_union_result_off(const abb_union_result *r);
+const int32_t *abb_union_result_items(const abb_union_result *r);
+const uint8_t *abb_union_result_w0(const abb_union_result *r);
+const uint8_t *abb_union_result_w1(const abb_union_result *r);
+double abb_union_result_ms(const abb_union_result *r);            /* device time of the kernels, CUDA events */
+void abb_union_result_free(abb_union_result *r);
+
 #ifdef __cplusplus
 }
 #endif

@@ -463,7 +463,108 @@ def snapshot_identity():
     print(f"-> {out_dir} {sum(f.stat().st_size for f in out_dir.iterdir()) / 1024:.0f} KiB")
 
 
+def _ctx_doc(name, graph, scores, extra_nodes=()):
+    """Serialise a reference ContextGraph (only the fields effective-reach scoring reads) with the reference's answers."""
+    keep_node = ("capabilities", "agent", "cvss_score", "epss_score", "is_kev")
+    nodes = [[n.id, n.kind.value if hasattr(n.kind, "value") else str(n.kind), n.label, {k: n.metadata[k] for k in keep_node if k in n.metadata}]
+             for n in graph.nodes.values()]
+    edges = [[e.source, e.target, e.kind.value if hasattr(e.kind, "value") else str(e.kind), {k: e.metadata[k] for k in ("server",) if k in e.metadata}]
+             for e in graph.edges]
+    adjacency = {nid: [[e.source, e.target, e.kind.value if hasattr(e.kind, "value") else str(e.kind)] for e in lst] for nid, lst in graph.adjacency.items() if lst}
+    return {"name": name, "nodes": nodes, "edges": edges, "adjacency": adjacency,
+            "scores": {nid: s.as_breakdown() for nid, s in scores.items()},
+            "edge_scores": [e.metadata.get("effective_reach_score") for e in graph.edges],
+            "extra": [[nid, sc.as_breakdown()] for nid, sc in extra_nodes]}
+
+
+def effective_reach_golden():
+    """Pin agent_bom_b200.effective_reach against the reference's annotate_graph / compute on ContextGraphs built by the
+    reference (its own test fixtures, a seeded synthetic fleet with shared servers, and hand-wired corner cases)."""
+    import copy
+
+    from agent_bom.context_graph import ContextGraph, EdgeKind, GraphEdge, GraphNode, NodeKind, build_context_graph
+    from agent_bom.effective_reach import annotate_graph, compute
+
+    spec = importlib.util.spec_from_file_location("ref_test_effective_reach", REF / "tests" / "test_effective_reach.py")
+    ref_tests = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_tests)
+    docs = []
+    for name, builder in (("low_reach", ref_tests._low_reach_fixture), ("high_reach", ref_tests._high_reach_fixture)):
+        agents, blast = builder()
+        g = build_context_graph(agents, blast)
+        docs.append(_ctx_doc(name, g, annotate_graph(g)))
+    agents, blast = ref_tests._high_reach_fixture()
+    blast[0]["affected_agents"] = ["claude-desktop"]                     # tests/test_effective_reach.py:175-186
+    g = build_context_graph(agents, blast)
+    docs.append(_ctx_doc("high_reach_one_listed_agent", g, annotate_graph(g)))
+    snapshots = json.loads((REF / "tests" / "fixtures" / "effective_reach_snapshots.json").read_text())
+    assert docs[0]["scores"]["vuln:CVE-2099-LOW"] == snapshots["low_reach"] and docs[1]["scores"]["vuln:CVE-2099-HIGH"] == snapshots["high_reach"]
+
+    rng = random.Random(2262)
+    env_pool = ["AWS_ACCESS_KEY_ID", "AWS_SECRET_ACCESS_KEY", "GITHUB_TOKEN", "NPM_TOKEN", "DATABASE_URL", "OPENAI_API_KEY", "STRIPE_SECRET_KEY", "SLACK_BOT_TOKEN",
+                "INTERNAL_API_KEY", "SERVICE_PASSWORD", "SIGNING_SECRET", "HOME", "PATH", "EDITOR", "MY_SETTING", "DD_API_KEY", "REDIS_URL", "AUTH_TOKEN"]
+    tool_pool = [("run_shell", "Execute arbitrary shell commands", ["execute"]), ("list_files", "List files in a directory", ["read"]),
+                 ("http_get", "Fetch a URL", ["network"]), ("write_file", "Write a file to disk", ["write"]), ("delete_rows", "Delete rows from a table", ["delete"]),
+                 ("grant_role", "Grant an IAM role", ["admin"]), ("login", "Authenticate a user", ["auth"]), ("search_docs", "Search indexed documents", ["read"]),
+                 ("noop", "Does nothing in particular", []), ("multi", "Read then write then run", ["read", "write", "execute"])]
+    server_pool = [f"srv-{i:02d}" for i in range(14)]
+    fleet = []
+    for a in range(40):
+        servers = []
+        for sname in rng.sample(server_pool, rng.randint(1, 4)):
+            env = {k: "x" for k in rng.sample(env_pool, rng.randint(0, 5))}
+            tools = [{"name": t[0], "description": t[1], "capabilities": list(t[2])} for t in rng.sample(tool_pool, rng.randint(0, 4))]
+            servers.append({"name": sname, "command": "node x.js", "transport": "stdio", "env": env, "tools": tools, "packages": [{"name": "left-pad", "version": "1.3.0"}]})
+        fleet.append({"name": f"agent-{a:02d}", "type": "custom", "status": "configured", "mcp_servers": servers})
+    blast = []
+    for v in range(120):
+        aff_agents = [f"agent-{i:02d}" for i in rng.sample(range(40), rng.randint(1, 6))]
+        blast.append({"vulnerability_id": f"CVE-2031-{v:04d}", "package": "left-pad", "severity": rng.choice(["critical", "high", "medium", "low"]),
+                      "cvss_score": rng.choice([None, 0, 3.1, 5.5, 6.5, 7.8, 9.8, 10.0, 11.5]), "epss_score": rng.choice([None, 0.0, 0.013, 0.2, 0.57, 0.92, 1.4]),
+                      "is_kev": rng.random() < 0.2, "affected_agents": aff_agents, "affected_servers": rng.sample(server_pool, rng.randint(1, 3))})
+    g = build_context_graph(copy.deepcopy(fleet), copy.deepcopy(blast))
+    docs.append(_ctx_doc("fleet_40", g, annotate_graph(g)))
+
+    # hand-wired corner cases on the reference's own container
+    g = ContextGraph()
+    for nid, kind, label, meta in (
+            ("agent:a", NodeKind.AGENT, "a", {}), ("agent:b", NodeKind.AGENT, "b", {}), ("agent:c", NodeKind.AGENT, "c", {}),
+            ("server:a:s", NodeKind.SERVER, "s", {"agent": "a"}), ("server:b:s", NodeKind.SERVER, "s", {"agent": "b"}), ("server:x", NodeKind.SERVER, "lonely", {}),
+            ("tool:1", NodeKind.TOOL, "t-exec", {"capabilities": ["read", "execute"]}), ("tool:2", NodeKind.TOOL, "t-none", {"capabilities": []}),
+            ("tool:3", NodeKind.TOOL, "t-unknown", {"capabilities": ["teleport"]}), ("tool:4", NodeKind.TOOL, "t-exec", {"capabilities": ["admin"]}),
+            ("cred:1", NodeKind.CREDENTIAL, "AWS_KEY", {}), ("cred:2", NodeKind.CREDENTIAL, "", {}), ("cred:3", NodeKind.CREDENTIAL, "path", {}),
+            ("cred:4", NodeKind.CREDENTIAL, " github_token ", {}),
+            ("vuln:1", NodeKind.VULNERABILITY, "V1", {"cvss_score": 7.5, "epss_score": 0.3, "is_kev": False}),
+            ("vuln:2", NodeKind.VULNERABILITY, "V2", {"cvss_score": "9.1", "epss_score": None, "is_kev": 1}),
+            ("vuln:3", NodeKind.VULNERABILITY, "V3-unattached", {}), ("vuln:4", NodeKind.VULNERABILITY, "V4-ghost-server", {"cvss_score": 4.0})):
+        g.add_node(GraphNode(id=nid, kind=kind, label=label, metadata=meta))
+    for s, t, k, meta in (
+            ("agent:a", "server:a:s", EdgeKind.USES, {}), ("agent:b", "server:b:s", EdgeKind.USES, {}), ("agent:c", "server:x", EdgeKind.USES, {}),
+            ("server:a:s", "tool:1", EdgeKind.PROVIDES, {}), ("server:a:s", "tool:2", EdgeKind.PROVIDES, {}), ("server:b:s", "tool:3", EdgeKind.PROVIDES, {}),
+            ("server:x", "tool:4", EdgeKind.PROVIDES, {}), ("server:a:s", "cred:1", EdgeKind.EXPOSES, {}), ("server:a:s", "cred:2", EdgeKind.EXPOSES, {}),
+            ("server:b:s", "cred:3", EdgeKind.EXPOSES, {}), ("server:x", "cred:4", EdgeKind.EXPOSES, {}),
+            ("server:a:s", "vuln:1", EdgeKind.VULNERABLE_TO, {}), ("server:x", "vuln:1", EdgeKind.VULNERABLE_TO, {}), ("server:b:s", "vuln:2", EdgeKind.VULNERABLE_TO, {}),
+            ("server:ghost", "vuln:4", EdgeKind.VULNERABLE_TO, {}), ("agent:a", "agent:b", EdgeKind.SHARES_SERVER, {"server": "s"}),
+            ("agent:a", "agent:c", EdgeKind.SHARES_SERVER, {"server": "other"}), ("agent:b", "agent:c", EdgeKind.SHARES_CREDENTIAL, {"credential": "AWS_KEY"}),
+            ("tool:1", "server:b:s", EdgeKind.PROVIDES, {})):               # a PROVIDES pointing INTO a server: its mirrored twin sits in the server's adjacency
+        g.add_edge(GraphEdge(source=s, target=t, kind=k, metadata=meta))
+    g.adjacency["server:x"].append(GraphEdge(source="server:x", target="agent:b", kind=EdgeKind.USES))      # hand-wired, not in graph.edges (:347-352)
+    g.adjacency["server:ghost"].append(GraphEdge(source="server:ghost", target="tool:1", kind=EdgeKind.PROVIDES))
+    extra = [(nid, compute(g.nodes[nid], g)) for nid in ("server:a:s", "agent:a")]      # non-vulnerability nodes get the degenerate score
+    docs.append(_ctx_doc("hand_wired", g, annotate_graph(g), extra))
+
+    path = OUT / "effective_reach.json.gz"
+    with gzip.GzipFile(path, "wb", mtime=0) as fh:
+        fh.write(json.dumps(docs, separators=(",", ":"), sort_keys=True).encode())
+    for d in docs:
+        print(f"effective_reach {d['name']}: {len(d['nodes'])} nodes {len(d['edges'])} edges {len(d['scores'])} scored")
+    print(f"-> {path} {path.stat().st_size / 1024:.0f} KiB")
+
+
 def main():
+    if "--effective-reach-only" in sys.argv:
+        effective_reach_golden()
+        return
     if "--snapshot-only" in sys.argv:
         snapshot_identity()
         return
@@ -475,6 +576,7 @@ def main():
     estate_identity()
     builder_identity()
     snapshot_identity()
+    effective_reach_golden()
     rng = random.Random(20260921)
     run_battery("kat_schema", kat_schema(), rng, small=True)
     run_battery("kat_directed", kat_directed(), rng, small=True)
