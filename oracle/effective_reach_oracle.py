@@ -2,7 +2,7 @@
 
 TEST INFRASTRUCTURE ONLY.  Nothing in the product imports this; tests check the CUDA path
 (``agent_bom_b200.effective_reach``) against it and it is itself pinned against the unmodified reference's answers in
-``tests/golden/effective_reach.json.gz`` (``oracle/make_golden.py --effective-reach-only``), which include the
+``tests/golden/context/effective_reach.json.gz`` (``oracle/make_golden.py --effective-reach-only``), which include the
 reference's own snapshot fixture ``tests/fixtures/effective_reach_snapshots.json``.
 
 Follows ``/root/reference/src/agent_bom/effective_reach.py``: weights :61-69, ``_credential_tier`` :144-169,

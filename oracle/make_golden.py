@@ -553,7 +553,8 @@ def effective_reach_golden():
     extra = [(nid, compute(g.nodes[nid], g)) for nid in ("server:a:s", "agent:a")]      # non-vulnerability nodes get the degenerate score
     docs.append(_ctx_doc("hand_wired", g, annotate_graph(g), extra))
 
-    path = OUT / "effective_reach.json.gz"
+    path = OUT / "context" / "effective_reach.json.gz"
+    path.parent.mkdir(parents=True, exist_ok=True)
     with gzip.GzipFile(path, "wb", mtime=0) as fh:
         fh.write(json.dumps(docs, separators=(",", ":"), sort_keys=True).encode())
     for d in docs:

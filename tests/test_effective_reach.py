@@ -1,6 +1,6 @@
 """Effective-reach scoring: oracle vs the reference's answers (CPU), CUDA path vs both (GPU).
 
-``tests/golden/effective_reach.json.gz`` holds ContextGraphs built by the unmodified reference (its own two test
+``tests/golden/context/effective_reach.json.gz`` holds ContextGraphs built by the unmodified reference (its own two test
 fixtures — whose breakdowns equal the reference's checked-in snapshot file —, a seeded 40-agent fleet with shared
 servers, hand-wired corner cases) and the reference's ``annotate_graph`` / ``compute`` output for each.
 """
@@ -17,7 +17,7 @@ import pytest
 from agent_bom_b200.context_graph import ContextGraph, EdgeKind, GraphEdge, GraphNode, NodeKind
 from agent_bom_b200.effective_reach import ReachScore, credential_tier, max_capability_weight
 
-DOCS = json.loads(gzip.decompress((Path(__file__).parent / "golden" / "effective_reach.json.gz").read_bytes()))
+DOCS = json.loads(gzip.decompress((Path(__file__).parent / "golden" / "context" / "effective_reach.json.gz").read_bytes()))
 IDS = [d["name"] for d in DOCS]
 
 
