@@ -33,13 +33,13 @@ static inline unsigned nblk(int64_t n, int t) { return static_cast<unsigned>(std
 
 // sort (key,val) pairs by key, then drop adjacent duplicate keys; returns the unique count
 static int sort_unique_pairs(cudaStream_t st, unsigned long long *k_in, int32_t *v_in, unsigned long long *k_tmp, int32_t *v_tmp, int64_t n,
-                             int64_t *n_unique, bool unique) {
+                             int64_t *n_unique, bool unique, int end_bit = 64) {
     if (n == 0) { *n_unique = 0; return ABB_OK; }
     if (n >= (1ll << 31)) return fail(ABB_ERR_ARG, "reach pipeline limited to 2^31 pairs per batch");
     size_t tb = 0;
-    CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tb, k_in, k_tmp, v_in, v_tmp, static_cast<int>(n), 0, 64, st));
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tb, k_in, k_tmp, v_in, v_tmp, static_cast<int>(n), 0, end_bit, st));
     Tmp t; if (int rc = t.alloc(tb)) return rc;
-    CUDA_TRY(cub::DeviceRadixSort::SortPairs(t.p, tb, k_in, k_tmp, v_in, v_tmp, static_cast<int>(n), 0, 64, st));
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(t.p, tb, k_in, k_tmp, v_in, v_tmp, static_cast<int>(n), 0, end_bit, st));
     g_launches++;
     if (!unique) {
         CUDA_TRY(cudaMemcpyAsync(k_in, k_tmp, static_cast<size_t>(n) * 8, cudaMemcpyDeviceToDevice, st));

@@ -73,7 +73,9 @@ extern "C" int abb_group_union_host(int device, int64_t n_groups, const int64_t 
         CUDA_TRY(cudaGetLastError());
     }
     int64_t AU = 0;
-    if (int rc = sort_unique_pairs(st, k1.as<unsigned long long>(), v1.as<int32_t>(), k2.as<unsigned long long>(), v2.as<int32_t>(), A0, &AU, true)) return rc;
+    int group_bits = 1;
+    while ((1ll << group_bits) < n_groups) group_bits++;          // only the key bits that vary take a radix pass
+    if (int rc = sort_unique_pairs(st, k1.as<unsigned long long>(), v1.as<int32_t>(), k2.as<unsigned long long>(), v2.as<int32_t>(), A0, &AU, true, 32 + group_bits)) return rc;
     CUDA_TRY(cudaMemsetAsync(counts.p, 0, static_cast<size_t>(n_groups + 2) * 8, st));
     if (AU) { reach_group_counts_kernel<<<nblk(AU, 256), 256, 0, st>>>(AU, k1.as<unsigned long long>(), counts.as<unsigned long long>()); g_launches++; }
     if (int rc = exclusive_scan_i64(st, counts.as<int64_t>(), poff.as<int64_t>(), n_groups + 1)) return rc;
