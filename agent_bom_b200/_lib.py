@@ -153,6 +153,7 @@ EXPORTS = {
     "abb_reach_vuln_agents": (vp, [vp]),
     "abb_reach_vuln_minhop": (vp, [vp]),
     "abb_reach_result_free": (None, [vp]),
+    "abb_bottleneck_host": (C.c_int, [vp, vp, i64, vp]),
     "abb_group_union_host": (C.c_int, [C.c_int, i64, vp, vp, i64, vp, vp, vp, vp, C.POINTER(vp)]),
     "abb_union_result_off": (vp, [vp]),
     "abb_union_result_items": (vp, [vp]),

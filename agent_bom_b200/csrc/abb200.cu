@@ -23,6 +23,7 @@
 #include "paths.cuh"
 #include "reach.cuh"
 #include "union.cuh"
+#include "centrality.cuh"
 #include "walk.cuh"
 
 using namespace abb;
@@ -1196,3 +1197,4 @@ extern "C" int abb_exposure_host(abb_graph *g, const int32_t *findings, int64_t 
 
 #include "reach_host.inl"
 #include "union_host.inl"
+#include "centrality_host.inl"

@@ -335,6 +335,14 @@ class DeviceGraph:
         finally:
             lib.abb_reach_result_free(res)
 
+    # ── sampled bottleneck score ────────────────────────────────────────
+    def bottleneck_scores(self, sources) -> np.ndarray:
+        """uint64 per node: over all sources, the number of BFS-tree paths the node lies strictly inside (``abb_bottleneck_host``)."""
+        src = _i32(sources)
+        out = np.zeros(self.n_nodes, dtype=np.uint64)
+        _lib.check(_lib.load().abb_bottleneck_host(self.handle, src.ctypes.data, int(src.shape[0]), out.ctypes.data))
+        return out
+
     # ── timing hooks used by bench.py ───────────────────────────────────
     def last_walk_ms(self) -> float:
         return float(_lib.load().abb_last_walk_ms(self.handle))

@@ -338,6 +338,26 @@ class UnifiedGraph:
             truncated = True
         return sub, depth_by_node, truncated
 
+    # ── centrality (reference container.py:540-567) ─────────────────────
+    def degree_centrality(self) -> dict[str, float]:
+        if not self.nodes:
+            return {}
+        c = self.csr
+        max_possible = max(len(self.nodes) - 1, 1)
+        deg = np.diff(c.fwd_off.astype(np.int64))
+        return {nid: int(deg[i]) / max_possible for i, nid in enumerate(self.nodes)}
+
+    def bottleneck_nodes(self, top_n: int = 5) -> list[tuple[str, float]]:
+        """BFS from the first 50 nodes over the forward adjacency (every entry, any depth); each node strictly inside a
+        first-discoverer path scores +1; scores are normalised by their sum and ranked, ties in node order."""
+        if not self.nodes:
+            return []
+        from ..backend import rank_bottlenecks
+
+        c = self.csr
+        sample = np.arange(min(50, c.n_real), dtype=np.int32)
+        return rank_bottlenecks(c, self.device_graph.bottleneck_scores(sample), top_n)
+
     # ── serialisation ───────────────────────────────────────────────────
     def to_dict(self) -> dict[str, Any]:
         def nd(n):

@@ -340,6 +340,14 @@ const int32_t *abb_reach_vuln_agents(const abb_reach_result *r); /* sorted by no
 const int32_t *abb_reach_vuln_minhop(const abb_reach_result *r);
 void abb_reach_result_free(abb_reach_result *r);
 
+/* ---- sampled bottleneck score -----------------------------------------------------------------------------------
+ * Replaces the BFS loop of UnifiedGraph.bottleneck_nodes (agent_bom/graph/container.py:548-567) and
+ * InMemoryBackend.bottleneck_nodes (agent_bom/graph_backend.py:127-155): from each source an unbounded forward BFS
+ * over every adjacency entry; each node strictly inside the first-discoverer path to a reached node gets +1.
+ * scores_out: host [n_nodes] — the un-normalised integer scores summed over all sources (the caller divides by their
+ * sum and sorts, as the reference does).  Sources must be nodes with a record (ghost / invalid sources add nothing). */
+int abb_bottleneck_host(abb_graph *g, const int32_t *sources, int64_t n_sources, uint64_t *scores_out);
+
 /* ---- per-group union of member item lists (effective-reach scoring) ------------------------------------------
  * Replaces the per-vulnerability reduction of agent_bom/effective_reach.py:372-426 (`compute`): for every group
  * (a vulnerability) over its members (the servers VULNERABLE_TO it, effective_reach.py:265-279) return

@@ -562,7 +562,80 @@ def effective_reach_golden():
     print(f"-> {path} {path.stat().st_size / 1024:.0f} KiB")
 
 
+def centrality_golden():
+    """Pin UnifiedGraph.degree_centrality / bottleneck_nodes (graph/container.py:540-567) on the walk-fixture graphs, and the whole
+    GraphBackend surface (graph_backend.py:41-155, 245-306) on op sequences replayed against the reference's InMemoryBackend."""
+    from agent_bom.graph_backend import InMemoryBackend, from_unified_graph
+
+    def guarded(fn):
+        try:
+            return {"value": fn()}
+        except KeyError as exc:
+            return {"key_error": exc.args[0]}
+
+    unified = {}
+    for name, g in (("kat_schema", kat_schema()), ("kat_directed", kat_directed()), ("kat_chain", kat_chain()), ("kat_reach_misc", kat_reach_misc()),
+                    ("kat_derived", kat_derived()), ("kat_probe", kat_probe()), ("mesh_inventory", mesh_inventory()), ("estate_150", estate(150)),
+                    ("estate_dense_40", estate(40, dense=(6, 8, 3)))):
+        unified[name] = {"degree": guarded(g.degree_centrality), "bottleneck_5": guarded(g.bottleneck_nodes),
+                         "bottleneck_12": guarded(lambda g=g: g.bottleneck_nodes(top_n=12)), "n_nodes": len(g.nodes)}
+        print(f"centrality {name}: {len(g.nodes)} nodes -> {str(unified[name]['bottleneck_5'])[:90]}")
+
+    rng = random.Random(548)
+    backends = []
+
+    def record(label, ops, sources, pairs):
+        b = InMemoryBackend()
+        for op in ops:
+            if op[0] == "n":
+                b.add_node(op[1], op[2], op[3], **op[4])
+            else:
+                b.add_edge(op[1], op[2], op[3], op[4], directed=op[5], **op[6])
+        ids = list(b._nodes) + sorted({t for nb in b._adj.values() for t in nb} - set(b._nodes))
+        doc = {"label": label, "ops": ops, "node_count": b.node_count(), "edge_count": b.edge_count(), "to_dict": b.to_dict(),
+               "centrality": guarded(b.centrality_scores), "bottleneck_5": guarded(b.bottleneck_nodes), "bottleneck_20": guarded(lambda: b.bottleneck_nodes(top_n=20)),
+               "neighbors": {nid: b.neighbors(nid) for nid in ids[:: max(1, len(ids) // 25)]},
+               "has_edge": [[s, t, b.has_edge(s, t)] for s, t in pairs[:40]],
+               "bfs": [[s, d, b.bfs(s, d)] for s in sources for d in (0, 1, 2, 4, 9)],
+               "shortest": [[s, t, b.shortest_path(s, t)] for s, t in pairs]}
+        backends.append(doc)
+        print(f"backend {label}: {b.node_count()} nodes {b.edge_count()} edges, {len(doc['bfs'])} bfs, {len(pairs)} pairs")
+
+    # seeded op soup: undirected and directed edges, re-added pairs (attributes overwritten, order kept), self loops, endpoints without a record
+    for label, n, m in (("soup-small", 14, 30), ("soup-mid", 120, 420), ("soup-sparse", 300, 340)):
+        names = [f"n{i:03d}" for i in range(n)]
+        ops = [["n", nid, rng.choice(["agent", "server", "tool"]), nid.upper(), {"tier": rng.randint(0, 3)} if rng.random() < 0.3 else {}] for nid in names]
+        rng.shuffle(ops)
+        pool = names + ["ghost-a", "ghost-b"]
+        for _ in range(m):
+            s, t = rng.choice(pool), rng.choice(pool)
+            ops.append(["e", s, t, rng.choice(["uses", "provides", "shares_server"]), rng.choice([1.0, 2.0, 3.5]), rng.random() < 0.4, {"note": "x"} if rng.random() < 0.2 else {}])
+        if label == "soup-small":
+            ops.append(["n", "n001", "agent", "re-added", {}])          # a node added twice keeps its place, takes the new attributes
+        sources = rng.sample(names, min(8, n)) + ["ghost-a", "nope"]
+        pairs = [[rng.choice(pool + ["nope"]), rng.choice(pool + ["nope"])] for _ in range(60)] + [[names[0], names[0]]]
+        record(label, ops, sources, pairs)
+    # a 70-node chain plus a star: deep trees, more than 50 nodes so the sample is a strict prefix
+    ops = [["n", f"c{i:02d}", "server", f"c{i}", {}] for i in range(70)] + [["n", "hub", "agent", "hub", {}]]
+    ops += [["e", f"c{i:02d}", f"c{i + 1:02d}", "uses", 1.0, True, {}] for i in range(69)] + [["e", "hub", f"c{i:02d}", "uses", 1.0, False, {}] for i in range(0, 70, 7)]
+    record("chain-and-star", ops, ["c00", "c35", "hub"], [["c00", "c69"], ["c69", "c00"], ["hub", "c33"], ["c10", "hub"]])
+    record("empty", [], ["x"], [["x", "y"]])
+    ug = mesh_inventory()
+    ref_b = from_unified_graph(ug, backend="memory")
+    bridge = {"n_nodes": ref_b.node_count(), "n_edges": ref_b.edge_count(), "to_dict": ref_b.to_dict(), "centrality": ref_b.centrality_scores(),
+              "bottleneck_10": guarded(lambda: ref_b.bottleneck_nodes(top_n=10)),
+              "bfs": [[s, 4, ref_b.bfs(s, 4)] for s in list(ug.nodes)[::9]]}
+    path = OUT / "context" / "centrality.json.gz"
+    path.parent.mkdir(parents=True, exist_ok=True)
+    with gzip.GzipFile(path, "wb", mtime=0) as fh:
+        fh.write(json.dumps({"unified": unified, "backends": backends, "mesh_bridge": bridge}, separators=(",", ":"), sort_keys=True).encode())
+    print(f"-> {path} {path.stat().st_size / 1024:.0f} KiB")
+
+
 def main():
+    if "--centrality-only" in sys.argv:
+        centrality_golden()
+        return
     if "--effective-reach-only" in sys.argv:
         effective_reach_golden()
         return
@@ -578,6 +651,7 @@ def main():
     builder_identity()
     snapshot_identity()
     effective_reach_golden()
+    centrality_golden()
     rng = random.Random(20260921)
     run_battery("kat_schema", kat_schema(), rng, small=True)
     run_battery("kat_directed", kat_directed(), rng, small=True)

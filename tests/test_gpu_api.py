@@ -162,14 +162,19 @@ def test_store_drop_in():
 
 
 def test_backend_drop_in():
+    """GraphBackend protocol shapes (graph_backend.py:23-38); the full behaviour is pinned in tests/test_backend_centrality.py."""
     from agent_bom_b200.backend import get_backend
 
     b = get_backend("b200")
+    for n in "aspvx":
+        b.add_node(n, "agent", n.upper())
     for s, t in (("a", "s"), ("s", "p"), ("p", "v"), ("a", "x")):
-        b.add_edge(s, t)
+        b.add_edge(s, t, "uses", directed=True)
     assert b.node_count() == 5 and b.edge_count() == 4 and b.has_edge("a", "s") and not b.has_edge("s", "a")
-    assert b.bfs("a", max_depth=2) == ["s", "x", "p"]
+    assert b.bfs("a", max_depth=2) == [["a", "s"], ["a", "x"], ["a", "s", "p"]]
     assert b.shortest_path("a", "v") == ["a", "s", "p", "v"] and b.shortest_path("v", "a") is None
+    b.add_edge("v", "a", "uses")                                        # undirected by default
+    assert b.shortest_path("v", "a") == ["v", "a"] and b.shortest_path("a", "v") == ["a", "v"]
     with pytest.raises(ValueError):
         get_backend("networkx")
 
