@@ -154,6 +154,13 @@ EXPORTS = {
     "abb_reach_vuln_minhop": (vp, [vp]),
     "abb_reach_result_free": (None, [vp]),
     "abb_bottleneck_host": (C.c_int, [vp, vp, i64, vp]),
+    "abb_lateral_paths_host": (C.c_int, [C.c_int, i32, vp, vp, vp, vp, vp, i64, vp, vp, i32, i64, C.POINTER(vp)]),
+    "abb_lateral_result_off": (vp, [vp]),
+    "abb_lateral_result_records": (vp, [vp]),
+    "abb_lateral_result_flags": (vp, [vp]),
+    "abb_lateral_result_width": (i32, [vp]),
+    "abb_lateral_result_ms": (C.c_double, [vp]),
+    "abb_lateral_result_free": (None, [vp]),
     "abb_group_union_host": (C.c_int, [C.c_int, i64, vp, vp, i64, vp, vp, vp, vp, C.POINTER(vp)]),
     "abb_union_result_off": (vp, [vp]),
     "abb_union_result_items": (vp, [vp]),

@@ -24,6 +24,7 @@
 #include "reach.cuh"
 #include "union.cuh"
 #include "centrality.cuh"
+#include "lateral.cuh"
 #include "walk.cuh"
 
 using namespace abb;
@@ -1198,3 +1199,4 @@ extern "C" int abb_exposure_host(abb_graph *g, const int32_t *findings, int64_t 
 #include "reach_host.inl"
 #include "union_host.inl"
 #include "centrality_host.inl"
+#include "lateral_host.inl"

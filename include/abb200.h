@@ -348,6 +348,27 @@ void abb_reach_result_free(abb_reach_result *r);
  * sum and sorts, as the reference does).  Sources must be nodes with a record (ghost / invalid sources add nothing). */
 int abb_bottleneck_host(abb_graph *g, const int32_t *sources, int64_t n_sources, uint64_t *scores_out);
 
+/* ---- lateral-movement path search -------------------------------------------------------------------------------
+ * Replaces the queue loop of find_lateral_paths (agent_bom/context_graph.py:397-477) for a batch of sources: a FIFO of
+ * simple paths over graph.adjacency, at most 100 recorded paths and 10 000 waiting paths per source, paths no longer
+ * than max_depth+1 nodes, in the reference's discovery order (the caller scores and sorts them, :574-593).
+ * adj_off[n_nodes+1] / adj_nbr / adj_kind: graph.adjacency rows in list order (edge kind 0..15);
+ * node_kind: 0 agent, 1 server, 2 credential, 3 tool, 4 vulnerability, 5 iam_role, 255 = id without a node record;
+ * node_key: agents: id of the label; credentials / tools: id of metadata["agent"], -1 when absent or empty; others ignored;
+ * sources / source_key: start node (-1 = unknown id: no paths) and the id of the source's agent name.
+ * max_depth 0..7.  max_pops: safety valve per source (<= 0: 50 M); a source that hits it has flag bit0 set and its result
+ * must be discarded.  Records: W+2 int32 words — length, edge kinds (4 bits per hop, first hop lowest), W node ids. */
+typedef struct abb_lateral_result abb_lateral_result;
+int abb_lateral_paths_host(int device, int32_t n_nodes, const int64_t *adj_off, const int32_t *adj_nbr, const uint8_t *adj_kind,
+                           const uint8_t *node_kind, const int32_t *node_key, int64_t n_sources, const int32_t *sources,
+                           const int32_t *source_key, int32_t max_depth, int64_t max_pops, abb_lateral_result **out);
+const int64_t *abb_lateral_result_off(const abb_lateral_result *r);      /* [n_sources+1] */
+const int32_t *abb_lateral_result_records(const abb_lateral_result *r);  /* [off[n_sources]][W+2] */
+const int32_t *abb_lateral_result_flags(const abb_lateral_result *r);    /* [n_sources] */
+int32_t abb_lateral_result_width(const abb_lateral_result *r);           /* W = max_depth + 2 */
+double abb_lateral_result_ms(const abb_lateral_result *r);
+void abb_lateral_result_free(abb_lateral_result *r);
+
 /* ---- per-group union of member item lists (effective-reach scoring) ------------------------------------------
  * Replaces the per-vulnerability reduction of agent_bom/effective_reach.py:372-426 (`compute`): for every group
  * (a vulnerability) over its members (the servers VULNERABLE_TO it, effective_reach.py:265-279) return

@@ -562,6 +562,94 @@ def effective_reach_golden():
     print(f"-> {path} {path.stat().st_size / 1024:.0f} KiB")
 
 
+def lateral_golden():
+    """Pin agent_bom_b200.lateral (and oracle/lateral_oracle.py) against the reference's find_lateral_paths on ContextGraphs the
+    reference built: its own effective-reach test fixtures, a seeded fleet with shared servers and credentials, hand-wired corner cases."""
+    import copy
+
+    from agent_bom.context_graph import ContextGraph, EdgeKind, GraphEdge, GraphNode, NodeKind, build_context_graph, find_lateral_paths
+
+    spec = importlib.util.spec_from_file_location("ref_test_effective_reach2", REF / "tests" / "test_effective_reach.py")
+    ref_tests = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_tests)
+
+    def doc_for(name, g, sources, depths):
+        keep_node = ("capabilities", "agent", "severity")
+        nodes = [[n.id, n.kind.value, n.label, {k: n.metadata[k] for k in keep_node if k in n.metadata}] for n in g.nodes.values()]
+        edges = [[e.source, e.target, e.kind.value, {k: e.metadata[k] for k in ("server", "credential") if k in e.metadata}] for e in g.edges]
+        adjacency = {nid: [[e.source, e.target, e.kind.value] for e in lst] for nid, lst in g.adjacency.items() if lst}
+        cases = []
+        for s in sources:
+            for d in depths:
+                found = find_lateral_paths(g, s, max_depth=d)
+                cases.append({"source": s, "max_depth": d, "paths": [
+                    {"source": p.source, "target": p.target, "hops": p.hops, "edges": [k.value for k in p.edges], "composite_risk": p.composite_risk,
+                     "summary": p.summary, "credential_exposure": p.credential_exposure, "tool_exposure": p.tool_exposure, "vuln_ids": p.vuln_ids} for p in found]})
+        print(f"lateral {name}: {len(nodes)} nodes {len(edges)} edges, {len(cases)} searches, {sum(len(c['paths']) for c in cases)} paths")
+        return {"name": name, "nodes": nodes, "edges": edges, "adjacency": adjacency, "cases": cases}
+
+    docs = []
+    agents, blast = ref_tests._high_reach_fixture()
+    g = build_context_graph(agents, blast)
+    docs.append(doc_for("high_reach", g, list(g.nodes) + ["agent:nobody"], (1, 2, 4, 6)))
+
+    rng = random.Random(397)
+    env_pool = ["AWS_ACCESS_KEY_ID", "GITHUB_TOKEN", "NPM_TOKEN", "DATABASE_URL", "OPENAI_API_KEY", "SLACK_BOT_TOKEN", "INTERNAL_API_KEY", "SERVICE_PASSWORD"]
+    tool_pool = [("run_shell", "Execute arbitrary shell commands", ["execute"]), ("list_files", "List files in a directory", ["read"]),
+                 ("http_get", "Fetch a URL", ["network"]), ("write_file", "Write a file to disk", ["write"]), ("exec_sql", "Execute SQL", ["execute"])]
+    server_pool = [f"srv-{i:02d}" for i in range(10)]
+    fleet = []
+    for a in range(24):
+        servers = []
+        for sname in rng.sample(server_pool, rng.randint(1, 3)):
+            env = {k: "x" for k in rng.sample(env_pool, rng.randint(0, 3))}
+            tools = [{"name": t[0], "description": t[1], "capabilities": list(t[2])} for t in rng.sample(tool_pool, rng.randint(0, 3))]
+            servers.append({"name": sname, "command": "node x.js", "transport": "stdio", "env": env, "tools": tools, "packages": []})
+        fleet.append({"name": f"agent-{a:02d}", "type": "custom", "status": "configured", "mcp_servers": servers})
+    blast = [{"vulnerability_id": f"CVE-2032-{v:03d}", "package": "p", "severity": rng.choice(["critical", "high", "medium", "low"]),
+              "affected_agents": [f"agent-{i:02d}" for i in rng.sample(range(24), rng.randint(1, 4))], "affected_servers": rng.sample(server_pool, 2)} for v in range(30)]
+    g = build_context_graph(copy.deepcopy(fleet), copy.deepcopy(blast))
+    some = [f"agent:agent-{i:02d}" for i in (0, 5, 11, 23)]
+    servers = [nid for nid in g.nodes if nid.startswith("server:")][:3]
+    tools = [nid for nid in g.nodes if nid.startswith("tool:")][:2]
+    docs.append(doc_for("fleet_24", g, some + servers + tools + [next(n for n in g.nodes if n.startswith("cred:"))], (1, 2, 3, 4)))
+    # a sparse fleet (few shared names): searches run deep instead of stopping at 100 one-hop sharing edges
+    fleet2 = []
+    for a in range(16):
+        servers = [{"name": f"own-{a}-{k}", "command": "x", "transport": "stdio", "env": {rng.choice(env_pool): "x"},
+                    "tools": [{"name": t[0], "description": t[1], "capabilities": list(t[2])} for t in rng.sample(tool_pool, 2)], "packages": []} for k in range(2)]
+        if a % 4 == 0:
+            servers.append({"name": "hub", "command": "x", "transport": "stdio", "env": {}, "tools": [], "packages": []})
+        fleet2.append({"name": f"a{a:02d}", "type": "custom", "status": "configured", "mcp_servers": servers})
+    g = build_context_graph(copy.deepcopy(fleet2), [])
+    docs.append(doc_for("fleet_sparse", g, [f"agent:a{i:02d}" for i in (0, 1, 4, 15)] + ["server:a00:hub"], (2, 4, 6)))
+
+    g = ContextGraph()
+    for nid, kind, label, meta in (
+            ("agent:a", NodeKind.AGENT, "a", {}), ("agent:b", NodeKind.AGENT, "b", {}), ("agent:a2", NodeKind.AGENT, "a", {}),
+            ("server:a:s", NodeKind.SERVER, "s", {"agent": "a"}), ("server:b:s", NodeKind.SERVER, "s", {"agent": "b"}),
+            ("tool:a", NodeKind.TOOL, "ta", {"agent": "a", "capabilities": ["execute"]}), ("tool:b", NodeKind.TOOL, "tb", {"agent": "b", "capabilities": ["execute"]}),
+            ("tool:none", NodeKind.TOOL, "tn", {"capabilities": ["read"]}), ("cred:shared", NodeKind.CREDENTIAL, "GITHUB_TOKEN", {"servers": []}),
+            ("cred:b", NodeKind.CREDENTIAL, "B_SECRET", {"agent": "b"}), ("vuln:1", NodeKind.VULNERABILITY, "CVE-1", {"severity": "high"}),
+            ("iam:r", NodeKind.IAM_ROLE, "role", {})):
+        g.add_node(GraphNode(id=nid, kind=kind, label=label, metadata=meta))
+    for s, t, k, meta in (
+            ("agent:a", "server:a:s", EdgeKind.USES, {}), ("agent:b", "server:b:s", EdgeKind.USES, {}), ("agent:a2", "server:a:s", EdgeKind.USES, {}),
+            ("server:a:s", "tool:a", EdgeKind.PROVIDES, {}), ("server:b:s", "tool:b", EdgeKind.PROVIDES, {}), ("server:a:s", "tool:none", EdgeKind.PROVIDES, {}),
+            ("server:a:s", "cred:shared", EdgeKind.EXPOSES, {}), ("server:b:s", "cred:shared", EdgeKind.EXPOSES, {}), ("server:b:s", "cred:b", EdgeKind.EXPOSES, {}),
+            ("server:b:s", "vuln:1", EdgeKind.VULNERABLE_TO, {}), ("agent:a", "agent:b", EdgeKind.SHARES_SERVER, {"server": "s"}),
+            ("agent:a", "agent:b", EdgeKind.SHARES_CREDENTIAL, {"credential": "GITHUB_TOKEN"}),       # parallel edge: the same node sequence arrives twice
+            ("iam:r", "agent:a", EdgeKind.ATTACHED_TO, {}), ("server:a:s", "ghost:x", EdgeKind.PROVIDES, {}), ("ghost:x", "agent:b", EdgeKind.USES, {})):
+        g.add_edge(GraphEdge(source=s, target=t, kind=k, metadata=meta))
+    docs.append(doc_for("hand_wired", g, list(g.nodes) + ["ghost:x"], (0, 1, 2, 3, 5, 7)))
+
+    path = OUT / "context" / "lateral.json.gz"
+    path.parent.mkdir(parents=True, exist_ok=True)
+    with gzip.GzipFile(path, "wb", mtime=0) as fh:
+        fh.write(json.dumps(docs, separators=(",", ":"), sort_keys=True).encode())
+    print(f"-> {path} {path.stat().st_size / 1024:.0f} KiB")
+
+
 def centrality_golden():
     """Pin UnifiedGraph.degree_centrality / bottleneck_nodes (graph/container.py:540-567) on the walk-fixture graphs, and the whole
     GraphBackend surface (graph_backend.py:41-155, 245-306) on op sequences replayed against the reference's InMemoryBackend."""
@@ -633,6 +721,9 @@ def centrality_golden():
 
 
 def main():
+    if "--lateral-only" in sys.argv:
+        lateral_golden()
+        return
     if "--centrality-only" in sys.argv:
         centrality_golden()
         return
@@ -652,6 +743,7 @@ def main():
     snapshot_identity()
     effective_reach_golden()
     centrality_golden()
+    lateral_golden()
     rng = random.Random(20260921)
     run_battery("kat_schema", kat_schema(), rng, small=True)
     run_battery("kat_directed", kat_directed(), rng, small=True)
