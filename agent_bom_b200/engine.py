@@ -377,10 +377,10 @@ def group_union(member_off, members, item_off, items, w0=None, w1=None, *, devic
     _lib.check(lib.abb_group_union_host(device, n_groups, moff.ctypes.data, mem.ctypes.data, n_members, ioff.ctypes.data, it.ctypes.data,
                                         a0.ctypes.data if a0 is not None else None, a1.ctypes.data if a1 is not None else None, C.byref(res)))
     try:
-        off = _view(lib.abb_union_result_off(res), n_groups + 1, np.int64).copy()
-        out = _view(lib.abb_union_result_items(res), int(off[-1]), np.int32).copy()
-        g0 = _view(lib.abb_union_result_w0(res), n_groups, np.uint8).copy()
-        g1 = _view(lib.abb_union_result_w1(res), n_groups, np.uint8).copy()
+        off = _view(lib.abb_union_result_off(res), n_groups + 1, np.int64)          # _view copies out of the result object
+        out = _view(lib.abb_union_result_items(res), int(off[-1]), np.int32)
+        g0 = _view(lib.abb_union_result_w0(res), n_groups, np.uint8)
+        g1 = _view(lib.abb_union_result_w1(res), n_groups, np.uint8)
         return off, out, g0, g1, float(lib.abb_union_result_ms(res))
     finally:
         lib.abb_union_result_free(res)
