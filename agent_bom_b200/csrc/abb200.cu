@@ -470,8 +470,8 @@ static int launch_global_variant(const WalkArgs &A, int slots, int sm_count, boo
 
 // Three tiers on one stream.  `A` carries spec/io and the first tier's work list (qlist/nq/nq_dev); every later
 // tier reads its work list and count from device memory, so nothing here waits for the GPU.
-//   S1  warp + shared-memory hash/queue            (<= 512 queue entries)
-//   G1  warp + global bitmap, bounded queue slot   (<= 64K queue entries), 24 warps per SM
+//   S1  warp + shared-memory hash/queue            (<= 256 queue entries by default; 512 with ABB_S1_CFG=0)
+//   G1  warp + global bitmap, bounded queue slot   (<= 64K queue entries), 40 warps per SM (ABB_G1_WARPS_PER_SM)
 //   GX  warp + global bitmap, whole-graph slot     (anything)
 // ctl: 12 counters — tier t uses ctl[4t .. 4t+3] = {work cursor, overflow count, fatal flag, -}
 static int enqueue_tiers(abb_graph *g, WalkArgs A, int64_t max_items, unsigned long long *ctl, int32_t *ov1, int32_t *ov2, cudaStream_t st) {
