@@ -12,7 +12,6 @@ mutation.  ``get_backend`` / ``from_context_graph`` / ``from_unified_graph`` mir
 from __future__ import annotations
 
 from collections import defaultdict
-from typing import Any
 
 import numpy as np
 

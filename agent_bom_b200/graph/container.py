@@ -30,7 +30,6 @@ from .schema import (
     ENTITY_VALUES,
     FINDING_CODES,
     REL_CODE,
-    REL_CODE_OTHER,
     SEVERITY_RANK,
     EntityType,
     enum_value,

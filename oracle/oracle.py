@@ -12,7 +12,6 @@ edges.  It is deliberately independent of the product's C++ CSR builder.
 from __future__ import annotations
 
 import ctypes as C
-import os
 import subprocess
 from dataclasses import dataclass
 from pathlib import Path

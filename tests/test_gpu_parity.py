@@ -10,7 +10,7 @@ from __future__ import annotations
 import numpy as np
 import pytest
 
-from golden_util import ALL_FIXTURES, edge_arrays, load, node_rank, oracle_graph, rank_path_rows, seeded_graph
+from golden_util import ALL_FIXTURES, edge_arrays, load, node_rank, rank_path_rows, seeded_graph
 from oracle import oracle as orc
 
 pytestmark = pytest.mark.gpu

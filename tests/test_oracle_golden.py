@@ -8,7 +8,6 @@ tests/test_graph_api.py:1585-1633) plus generator estates.  CPU-only.
 
 from __future__ import annotations
 
-import numpy as np
 import pytest
 
 from golden_util import ALL_FIXTURES, SMALL_FIXTURES, load, node_rank, oracle_graph, rank_path_rows
