@@ -85,3 +85,36 @@ def test_walk_spec_mapping():
     assert s.rel_mask == 0 and s.flags & _lib.WALK_MARK_ROOTS and s.flags & _lib.WALK_TRAVERSABLE_ONLY
     s = DG.spec_shortest_path()
     assert s.max_depth < 0 and s.flags & _lib.WALK_TARGET
+
+
+def test_next_row_entry_points_refuse_without_device():
+    """The §8(f) entry points (union reduction, lateral search, bottleneck score, backend traversals) have no CPU path either."""
+    from agent_bom_b200 import _lib
+    from agent_bom_b200.backend import get_backend
+    from agent_bom_b200.context_graph import ContextGraph, EdgeKind, GraphEdge, GraphNode, NodeKind
+    from agent_bom_b200.effective_reach import annotate_graph
+    from agent_bom_b200.engine import group_union
+    from agent_bom_b200.lateral import find_lateral_paths
+
+    if _lib.load().abb_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    refused = (_lib.AbbError, _lib.EngineUnavailable)
+    with pytest.raises(refused):
+        group_union([0, 1], [0], [0, 1], [5])
+    g = ContextGraph()
+    g.add_node(GraphNode("agent:a", NodeKind.AGENT, "a"))
+    g.add_node(GraphNode("agent:b", NodeKind.AGENT, "b"))
+    g.add_node(GraphNode("vuln:1", NodeKind.VULNERABILITY, "v"))
+    g.add_edge(GraphEdge("agent:a", "agent:b", EdgeKind.SHARES_SERVER))
+    with pytest.raises(refused):
+        find_lateral_paths(g, "agent:a")
+    with pytest.raises(refused):
+        annotate_graph(g)
+    assert "effective_reach" not in g.nodes["vuln:1"].metadata          # nothing was written by a half-run
+    b = get_backend("b200")
+    b.add_node("a", "agent", "a")
+    b.add_edge("a", "b", "uses")
+    with pytest.raises(refused):
+        b.bfs("a")
+    with pytest.raises(refused):
+        b.bottleneck_nodes()
