@@ -12,6 +12,7 @@ mutation.  ``get_backend`` / ``from_context_graph`` / ``from_unified_graph`` mir
 from __future__ import annotations
 
 from collections import defaultdict
+from typing import Protocol, runtime_checkable
 
 import numpy as np
 
@@ -20,6 +21,24 @@ from .graph import csr as csrmod
 from .graph.schema import ENTITY_CODE_GHOST, enum_value
 
 _SAMPLE = 50      # sources sampled by bottleneck_nodes (graph_backend.py:135)
+
+
+@runtime_checkable
+class GraphBackend(Protocol):
+    """The reference's protocol (graph_backend.py:23-38), restated so callers can ``isinstance``-check a backend."""
+
+    def add_node(self, node_id: str, kind: str, label: str, **metadata: object) -> None: ...
+    def add_edge(self, source: str, target: str, kind: str, weight: float = 1.0, *, directed: bool = False, **metadata: object) -> None: ...
+    def has_node(self, node_id: str) -> bool: ...
+    def has_edge(self, source: str, target: str) -> bool: ...
+    def neighbors(self, node_id: str) -> list[str]: ...
+    def bfs(self, source: str, max_depth: int = 4) -> list[list[str]]: ...
+    def shortest_path(self, source: str, target: str) -> list[str] | None: ...
+    def node_count(self) -> int: ...
+    def edge_count(self) -> int: ...
+    def to_dict(self) -> dict: ...
+    def centrality_scores(self) -> dict[str, float]: ...
+    def bottleneck_nodes(self, top_n: int = 5) -> list[tuple[str, float]]: ...
 
 
 class B200Backend:

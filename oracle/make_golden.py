@@ -624,6 +624,27 @@ def lateral_golden():
     g = build_context_graph(copy.deepcopy(fleet2), [])
     docs.append(doc_for("fleet_sparse", g, [f"agent:a{i:02d}" for i in (0, 1, 4, 15)] + ["server:a00:hub"], (2, 4, 6)))
 
+    # the scenarios of the reference's own TestLateralPaths (tests/test_context_graph.py:187-300), built with its helpers
+    spec2 = importlib.util.spec_from_file_location("ref_test_context_graph", REF / "tests" / "test_context_graph.py")
+    rt = importlib.util.module_from_spec(spec2)
+    spec2.loader.exec_module(rt)
+    scenarios = {
+        "shared_server": ([rt._agent(name="agent-a", servers=[rt._server(name="shared-srv")]), rt._agent(name="agent-b", servers=[rt._server(name="shared-srv")])], []),
+        "no_cycles": ([rt._agent(name="agent-a", servers=[rt._server(name="shared-srv", env={"API_KEY": "x"})]),
+                       rt._agent(name="agent-b", servers=[rt._server(name="shared-srv", env={"API_KEY": "y"})])], []),
+        "risk_scoring": ([rt._agent(name="agent-a", servers=[rt._server(name="srv", env={"SECRET_KEY": "x"})]), rt._agent(name="agent-b", servers=[rt._server(name="srv")])],
+                         [rt._blast(severity="critical", agents=["agent-a", "agent-b"], servers=["srv"])]),
+        "credential_along_path": ([rt._agent(name="agent-a", servers=[rt._server(name="srv", env={"TOKEN": "x"})]), rt._agent(name="agent-b", servers=[rt._server(name="srv")])], []),
+        "execute_tool": ([rt._agent(name="agent-a", servers=[rt._server(name="srv", tools=[rt._tool("run_shell", "Execute shell commands")])]),
+                          rt._agent(name="agent-b", servers=[rt._server(name="srv")])], []),
+        "cap_20_agents": ([rt._agent(name=f"agent-{i}", servers=[rt._server(name="shared")]) for i in range(20)], []),
+        "dense_15_agents": ([rt._agent(name=f"agent-{i}", servers=[rt._server(name="shared", env={"KEY": "x"}, tools=[rt._tool("exec", "run code")])]) for i in range(15)], []),
+    }
+    for label, (agents_data, blast_data) in scenarios.items():
+        g = build_context_graph(agents_data, blast_data)
+        first = "agent:agent-a" if "agent:agent-a" in g.nodes else "agent:agent-0"
+        docs.append(doc_for(f"reference_test_{label}", g, [first, "agent:nonexistent"], (0, 4)))
+
     g = ContextGraph()
     for nid, kind, label, meta in (
             ("agent:a", NodeKind.AGENT, "a", {}), ("agent:b", NodeKind.AGENT, "b", {}), ("agent:a2", NodeKind.AGENT, "a", {}),
