@@ -131,3 +131,75 @@ def sum_over_ranks(value: float, info: RankInfo, device: torch.device | str) -> 
 def barrier(info: RankInfo) -> None:
     if info.world > 1:
         dist.barrier()
+
+
+# ── dependency reach across ranks: the one place the path has a real exchange step (SURVEY.md §8e, a9 pass 2) ───────────
+REACH_KEYS = ("pkg_ids", "pkg_off", "pkg_agents", "pkg_minhop", "vuln_ids", "vuln_poff", "vuln_pkgs", "vuln_aoff", "vuln_agents", "vuln_minhop")
+
+
+def all_gather_ragged(arr: np.ndarray, info: RankInfo, device: torch.device | str) -> list[np.ndarray]:
+    """Every rank's 1-D array on every rank: one size exchange, one padded all-gather (NCCL over NVLink on GPUs, gloo on CPU)."""
+    a = np.ascontiguousarray(arr)
+    if info.world == 1:
+        return [a]
+    device = torch.device(device)
+    size = torch.tensor([a.shape[0]], dtype=torch.int64, device=device)
+    sizes = [torch.zeros_like(size) for _ in range(info.world)]
+    dist.all_gather(sizes, size)
+    counts = [int(s.item()) for s in sizes]
+    width = max(max(counts), 1)
+    buf = torch.zeros(width, dtype=torch.from_numpy(a[:0]).dtype, device=device)
+    if a.shape[0]:
+        buf[: a.shape[0]] = torch.from_numpy(a).to(device)
+    parts = [torch.empty_like(buf) for _ in range(info.world)]
+    dist.all_gather(parts, buf)
+    return [p[:c].cpu().numpy() for p, c in zip(parts, counts)]
+
+
+def merge_dependency_reach(partials: list[dict], node_rank) -> dict:
+    """Combine per-rank results of ``DeviceGraph.dependency_reach`` computed over disjoint agent shards.
+
+    Package and vulnerability tables are graph-constant (identical on every rank); what differs is who reaches what:
+    per package / vulnerability the agent lists are concatenated and re-sorted by id-string rank (the reference's
+    ``tuple(sorted(...))``, graph/dependency_reach.py:139-145,156-164), and the hop minimum is taken over the ranks that
+    reach it at all (a rank that does not reach it reports 0, which must not win the minimum)."""
+    node_rank = np.asarray(node_rank)
+    first = partials[0]
+    out = {k: first[k] for k in ("pkg_ids", "vuln_ids", "vuln_poff", "vuln_pkgs")}
+    for key_off, key_items, key_min, n_groups in (("pkg_off", "pkg_agents", "pkg_minhop", len(first["pkg_ids"])),
+                                                  ("vuln_aoff", "vuln_agents", "vuln_minhop", len(first["vuln_ids"]))):
+        groups, items, big = [], [], np.full(n_groups, np.iinfo(np.int32).max, dtype=np.int64)
+        for p in partials:
+            counts = np.diff(np.asarray(p[key_off], dtype=np.int64))
+            groups.append(np.repeat(np.arange(n_groups, dtype=np.int64), counts))
+            items.append(np.asarray(p[key_items], dtype=np.int32))
+            reached = counts > 0
+            big[reached] = np.minimum(big[reached], np.asarray(p[key_min], dtype=np.int64)[reached])
+        grp = np.concatenate(groups) if groups else np.zeros(0, np.int64)
+        itm = np.concatenate(items) if items else np.zeros(0, np.int32)
+        order = np.lexsort((node_rank[itm], grp))
+        off = np.zeros(n_groups + 1, dtype=np.int64)
+        off[1:] = np.cumsum(np.bincount(grp, minlength=n_groups))
+        out[key_off], out[key_items] = off, itm[order]
+        out[key_min] = np.where(big == np.iinfo(np.int32).max, 0, big).astype(np.int32)
+    return out
+
+
+def dependency_reach_sharded(local_reach, agents, node_rank, info: RankInfo, device: torch.device | str) -> dict:
+    """``compute_dependency_reach`` with the agent BFSs split across ranks.
+
+    ``local_reach(agent_shard) -> dict`` is this rank's device call (``lambda a: dg.dependency_reach(a, REACH_MASK,
+    VULN_PKG_MASK)``).  Pass 1 (a BFS per agent) needs no communication; pass 2's per-package union / minimum is the
+    exchange: every rank's ragged agent lists are all-gathered and merged, so every rank ends with the full answer."""
+    agents = np.ascontiguousarray(agents, dtype=np.int32)
+    lo, hi = shard_bounds(len(agents), info.world, info.rank)
+    mine = local_reach(agents[lo:hi])
+    if info.world == 1:
+        return {k: np.asarray(mine[k]) for k in REACH_KEYS}
+    gathered = {k: all_gather_ragged(np.asarray(mine[k]), info, device) for k in ("pkg_off", "pkg_agents", "pkg_minhop", "vuln_aoff", "vuln_agents", "vuln_minhop")}
+    partials = []
+    for r in range(info.world):
+        p = {k: np.asarray(mine[k]) for k in ("pkg_ids", "vuln_ids", "vuln_poff", "vuln_pkgs")}
+        p.update({k: gathered[k][r] for k in gathered})
+        partials.append(p)
+    return merge_dependency_reach(partials, node_rank)

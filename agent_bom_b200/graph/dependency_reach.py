@@ -52,13 +52,25 @@ class ReachabilityReport:
         return tuple(sorted(v.vulnerability_id for v in self.vulnerabilities.values() if v.reachable))
 
 
-def compute_dependency_reach(graph) -> ReachabilityReport:
-    """``graph`` is an ``agent_bom_b200.graph.UnifiedGraph`` (use ``UnifiedGraph.from_graph`` to adopt a reference graph)."""
+def compute_dependency_reach(graph, *, rank_info=None, collective_device=None) -> ReachabilityReport:
+    """``graph`` is an ``agent_bom_b200.graph.UnifiedGraph`` (use ``UnifiedGraph.from_graph`` to adopt a reference graph).
+
+    With ``rank_info`` (``agent_bom_b200.dist.init_from_env()``) of a multi-rank job, every rank holding the same graph, the
+    per-agent BFSs are split across ranks and the per-package union / minimum is exchanged with one all-gather
+    (``dist.dependency_reach_sharded``); every rank returns the full report."""
     csr = graph.csr
     ids = csr.node_ids
     agents = np.asarray([csr.idx(n.id) for n in graph.nodes.values() if enum_value(n.entity_type) == EntityType.AGENT.value], dtype=np.int32)
-    out = graph.device_graph.dependency_reach(agents, REACH_MASK, VULN_PKG_MASK)
+    if rank_info is not None and rank_info.world > 1:
+        from ..dist import dependency_reach_sharded
+
+        dg = graph.device_graph
+        out = dependency_reach_sharded(lambda shard: dg.dependency_reach(shard, REACH_MASK, VULN_PKG_MASK), agents, csr.node_rank, rank_info,
+                                       collective_device if collective_device is not None else f"cuda:{graph.device}")
+    else:
+        out = graph.device_graph.dependency_reach(agents, REACH_MASK, VULN_PKG_MASK)
     packages: dict[str, PackageReachability] = {}
+    out = {k: np.asarray(v) for k, v in out.items()}
     po, pa, pm = out["pkg_off"].tolist(), out["pkg_agents"].tolist(), out["pkg_minhop"].tolist()
     for i, p in enumerate(out["pkg_ids"].tolist()):
         packages[ids[p]] = PackageReachability(ids[p], tuple(ids[a] for a in pa[po[i]: po[i + 1]]), pm[i])

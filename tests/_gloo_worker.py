@@ -30,3 +30,24 @@ assert abdist.max_over_ranks(float(info.rank), info, "cpu") == float(info.world 
 abdist.barrier(info)
 sys.stdout.write("rank%d-ok\n" % info.rank)
 sys.stdout.flush()
+
+# ── dependency reach with the agents split across ranks: the oracle stands in for each rank's device call ──────────────
+from agent_bom_b200.graph.schema import REACH_MASK, VULN_PKG_MASK  # noqa: E402
+from oracle import oracle as orc  # noqa: E402
+
+og = orc.build_csr(ref.n_nodes, est.src, est.dst, est.rel, est.flags, est.node_type)
+agents = np.flatnonzero(est.node_type == 0).astype(np.int32)
+
+
+def local(shard):
+    return orc.dependency_reach(og, shard, REACH_MASK, VULN_PKG_MASK, est.node_rank)
+
+
+merged = abdist.dependency_reach_sharded(local, agents, est.node_rank, info, "cpu")
+whole = local(agents)
+for key in abdist.REACH_KEYS:
+    assert np.array_equal(np.asarray(merged[key]), np.asarray(whole[key])), key
+assert len(agents) > 10 and int(np.asarray(whole["pkg_off"])[-1]) > 0
+abdist.barrier(info)
+sys.stdout.write("rank%d-reach-ok\n" % info.rank)
+sys.stdout.flush()

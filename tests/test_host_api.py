@@ -102,6 +102,24 @@ def test_shard_bounds_cover_everything_once():
             assert max(sizes) - min(sizes) <= 1
 
 
+@pytest.mark.parametrize("name", ["kat_chain", "kat_reach_misc", "mesh_inventory", "estate_dense_40"])
+def test_dependency_reach_partials_merge_to_the_whole(name):
+    """a9 across ranks: agent shards of any shape merge (union by id rank, minimum over reaching shards only) to the unsplit answer."""
+    from agent_bom_b200.dist import REACH_KEYS, merge_dependency_reach
+    from agent_bom_b200.graph.schema import REACH_MASK, VULN_PKG_MASK
+
+    doc = load(name)
+    og = oracle_graph(name)
+    rank = node_rank(doc["node_ids"])
+    agents = np.flatnonzero(og.node_type == 0).astype(np.int32)
+    whole = orc.dependency_reach(og, agents, REACH_MASK, VULN_PKG_MASK, rank)
+    for cuts in ([0, len(agents)], [0, 1, len(agents)], [0, len(agents) // 3, len(agents) // 3, len(agents)], list(range(len(agents) + 1))[:6] + [len(agents)]):
+        parts = [orc.dependency_reach(og, agents[a:b], REACH_MASK, VULN_PKG_MASK, rank) for a, b in zip(cuts, cuts[1:])]
+        merged = merge_dependency_reach(parts, rank)
+        for key in REACH_KEYS:
+            assert np.array_equal(np.asarray(merged[key]), np.asarray(whole[key])), (key, cuts)
+
+
 def test_gloo_world2_broadcast_and_shard():
     """N>1 plumbing on CPU: rank 0's CSR reaches rank 1 bit-identically over a world_size-2 gloo group; shards tile the source list."""
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
@@ -109,3 +127,5 @@ def test_gloo_world2_broadcast_and_shard():
                            str(ROOT / "tests" / "_gloo_worker.py")], capture_output=True, text=True, env=env, timeout=300)
     assert proc.returncode == 0, proc.stdout + proc.stderr
     assert "rank0-ok" in proc.stdout and "rank1-ok" in proc.stdout
+    # dependency reach split over the two ranks (per-package union / minimum exchanged by all-gather) equals the unsplit answer
+    assert "rank0-reach-ok" in proc.stdout and "rank1-reach-ok" in proc.stdout
