@@ -76,6 +76,8 @@ EXPORTS = {
     "abb_graph_bytes": (i64, [vp]),
     "abb_graph_set_dedup": (C.c_int, [vp, C.c_int]),
     "abb_graph_device": (C.c_int, [vp]),
+    "abb_graph_set_option": (C.c_int, [vp, C.c_char_p, i64]),
+    "abb_graph_get_option": (i64, [vp, C.c_char_p]),
     "abb_graph_free": (None, [vp]),
     "abb_spec_impact_of": (WalkSpec, [i32]),
     "abb_spec_bfs": (WalkSpec, [i32, i32]),
@@ -88,6 +90,7 @@ EXPORTS = {
     "abb_launch_count": (i64, []),
     "abb_last_walk_ms": (C.c_float, [vp]),
     "abb_last_walk_stats": (C.c_int, [vp, vp]),
+    "abb_last_walk_tier_counts": (C.c_int, [vp, vp]),
     "abb_last_paths_ms": (C.c_float, [vp]),
     "abb_walk_host": (C.c_int, [vp, C.POINTER(WalkSpec), vp, vp, vp, i64, C.POINTER(vp)]),
     "abb_walk_result_queries": (i64, [vp]),

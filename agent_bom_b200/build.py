@@ -17,7 +17,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libabb200.so"
 SOURCES = [CSRC / "abb200.cu"]
-DEPS = [CSRC / n for n in ("abb200.cu", "walk.cuh", "paths.cuh", "reach.cuh", "reach_host.inl")] + [PKG.parent / "include" / "abb200.h"]
+DEPS = sorted(p for p in CSRC.iterdir() if p.suffix in (".cu", ".cuh", ".inl", ".h")) + sorted((PKG.parent / "include").glob("*.h"))
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

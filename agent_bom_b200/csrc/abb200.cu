@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -26,6 +27,7 @@
 #include "centrality.cuh"
 #include "lateral.cuh"
 #include "walk.cuh"
+#include "walkb.cuh"
 
 using namespace abb;
 
@@ -108,6 +110,10 @@ extern "C" int abb_csr_build_host(int32_t n_nodes, int64_t n_edges, const int32_
     return ABB_OK;
 }
 
+constexpr int CTL_WORDS = 64;        // 5 tiers x 4 counters, twice (canonical walks at 0, individual walks at CTL_SET)
+constexpr int CTL_SET = 32;
+constexpr int CTL_FATAL = 4 * 4 + 2;  // last tier's fatal flag inside a set
+
 // ------------------------------------------------------------------ device buffers
 struct DevBuf {
     void *p = nullptr; size_t cap = 0;
@@ -179,7 +185,12 @@ struct abb_graph {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool walk_timed = false, paths_timed = false;
     // tier bookkeeping
-    DevBuf ctl, ov1, ov2;
+    DevBuf ctl, ov1, ov2, ov3, ov4;
+    // block tiers (walkb.cuh): mid = 8 warps, queue + table in shared memory; big = 32 warps, 192 KB table, queue in a global scratch slot per block
+    int block_tiers = 3;              // bit 0: mid tier, bit 1: big tier (ABB_BLOCK_TIERS / abb_graph_set_option)
+    int mid_slots = 8192, mid_qcap = 4096, big_slots = 49152, big_qcap = 36864;
+    int big_grid = 0;
+    DevBuf b_gq, b_gpar, b_gdep;
     // tier G1: many per-warp slots (bitmap over all nodes + a bounded queue); tier GX: a few slots that can hold a whole-graph walk
     DevBuf g_bitmap, g_queue, g_par, g_dep;
     int g_slots = 0; int64_t g_words = 0, g_qcap = 0;
@@ -229,7 +240,7 @@ static int graph_finish_init(abb_graph *g) {
     CUDA_TRY(cudaStreamCreateWithFlags(&g->copy_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&g->ev_copy, cudaEventDisableTiming));
     for (auto &e : g->ev) CUDA_TRY(cudaEventCreate(&e));
-    if (int rc = g->ctl.ensure(64 * sizeof(unsigned long long))) return rc;
+    if (int rc = g->ctl.ensure(CTL_WORDS * sizeof(unsigned long long))) return rc;
     const int64_t n = g->v.n;
     g->g_words = (n + 31) / 32 + 1;
     // tier G1: 40 warps per SM (latency-bound pointer chasing wants every warp it can get), queue bounded at 64K entries
@@ -256,6 +267,8 @@ static int graph_finish_init(abb_graph *g) {
         CUDA_TRY(cudaMemset(g->x_bitmap.p, 0, sl * g->g_words * 4));
     }
     if (const char *e = getenv("ABB_DEDUP")) g->dedup_enabled = atoi(e) != 0;
+    if (const char *e = getenv("ABB_BLOCK_TIERS")) g->block_tiers = atoi(e) & 3;
+    g->big_grid = g->sm_count;
     if (const char *e = getenv("ABB_S1_CFG")) g->s1_cfg = atoi(e);
     if (const char *e = getenv("ABB_ZEROCOPY")) g->zero_copy = atoi(e) != 0;
     if (const char *e = getenv("ABB_ALIGN_DIRECT")) g->align_direct = atoi(e) != 0;
@@ -350,6 +363,35 @@ extern "C" int abb_graph_set_dedup(abb_graph *g, int enabled) {
 }
 extern "C" int abb_graph_device(const abb_graph *g) { return g ? g->device : -1; }
 
+// Tuning / test switches of a graph handle.  Results never depend on them (every tier is bit-identical; the GPU tests
+// run the suite with the block tiers on, off and shrunk so that every hand-off between tiers is exercised).
+extern "C" int abb_graph_set_option(abb_graph *g, const char *name, int64_t value) {
+    if (!g || !name) return fail(ABB_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(g->mu);
+    const std::string k(name);
+    if (k == "dedup") g->dedup_enabled = value != 0;
+    else if (k == "block_tiers") g->block_tiers = static_cast<int>(value) & 3;
+    else if (k == "mid_qcap") {
+        if (value < 32 || value > 4096) return fail(ABB_ERR_ARG, "mid_qcap must be in [32, 4096]");
+        g->mid_qcap = static_cast<int>(value);
+    } else if (k == "big_qcap") {
+        if (value < 32 || value > 36864) return fail(ABB_ERR_ARG, "big_qcap must be in [32, 36864]");
+        g->big_qcap = static_cast<int>(value);
+    } else if (k == "zero_copy") g->zero_copy = value != 0;
+    else return fail(ABB_ERR_ARG, "unknown option '%s'", name);
+    return ABB_OK;
+}
+extern "C" int64_t abb_graph_get_option(const abb_graph *g, const char *name) {
+    if (!g || !name) return -1;
+    const std::string k(name);
+    if (k == "dedup") return g->dedup_enabled;
+    if (k == "block_tiers") return g->block_tiers;
+    if (k == "mid_qcap") return g->mid_qcap;
+    if (k == "big_qcap") return g->big_qcap;
+    if (k == "zero_copy") return g->zero_copy;
+    return -1;
+}
+
 extern "C" void abb_graph_free(abb_graph *g) {
     if (!g) return;
     DeviceGuard dg(g->device);
@@ -357,7 +399,7 @@ extern "C" void abb_graph_free(abb_graph *g) {
     if (g->copy_stream) { cudaStreamSynchronize(g->copy_stream); cudaStreamDestroy(g->copy_stream); }
     if (g->ev_copy) cudaEventDestroy(g->ev_copy);
     for (auto &e : g->ev) if (e) cudaEventDestroy(e);
-    for (DevBuf *b : {&g->ctl, &g->ov1, &g->ov2, &g->g_bitmap, &g->g_queue, &g->g_par, &g->g_dep, &g->x_bitmap, &g->x_queue, &g->x_par, &g->x_dep, &g->dd_sig, &g->dd_ssig, &g->dd_q, &g->dd_sq, &g->dd_head, &g->dd_gid, &g->dd_hp, &g->dd_glen, &g->dd_goff, &g->dd_arena, &g->dd_memoff, &g->dd_memsrc, &g->dd_memstate, &g->dd_indiv, &g->dd_cnt, &g->dd_tmp, &g->dd_gstart, &g->dd_gcount, &g->dd_gmaxd, &g->dd_gflags, &g->dd_ghist, &g->identity_rank, &g->d_roots, &g->d_root_off,
+    for (DevBuf *b : {&g->ctl, &g->ov1, &g->ov2, &g->ov3, &g->ov4, &g->b_gq, &g->b_gpar, &g->b_gdep, &g->g_bitmap, &g->g_queue, &g->g_par, &g->g_dep, &g->x_bitmap, &g->x_queue, &g->x_par, &g->x_dep, &g->dd_sig, &g->dd_ssig, &g->dd_q, &g->dd_sq, &g->dd_head, &g->dd_gid, &g->dd_hp, &g->dd_glen, &g->dd_goff, &g->dd_arena, &g->dd_memoff, &g->dd_memsrc, &g->dd_memstate, &g->dd_indiv, &g->dd_cnt, &g->dd_tmp, &g->dd_gstart, &g->dd_gcount, &g->dd_gmaxd, &g->dd_gflags, &g->dd_ghist, &g->identity_rank, &g->d_roots, &g->d_root_off,
                       &g->d_targets, &g->d_qstart, &g->d_qcount, &g->d_qmaxd, &g->d_qflags, &g->d_qestart, &g->d_qecount, &g->d_qhist, &g->d_nodes,
                       &g->d_parent, &g->d_depth, &g->d_edges, &g->d_totals, &g->p_findings, &g->p_counts, &g->p_off, &g->p_hops, &g->p_rels,
                       &g->p_ncred, &g->p_ntool, &g->p_scan_tmp, &g->srv_cred, &g->srv_tool, &g->pl_cnt, &g->pl_off, &g->pl_vs, &g->pl_rel, &g->pl_rows, &g->pl_roff, &g->pl_toff, &g->pl_need, &g->pl_ulist, &g->pl_nu, &g->pt_cnt, &g->pt_off, &g->pt_off_node, &g->pt_cnt_node, &g->pt_row, &g->pt_rel})
@@ -468,26 +510,83 @@ static int launch_global_variant(const WalkArgs &A, int slots, int sm_count, boo
     return ABB_OK;
 }
 
-// Three tiers on one stream.  `A` carries spec/io and the first tier's work list (qlist/nq/nq_dev); every later
+template <int W, bool QSM, bool PAR, bool META, int MINB>
+static int launch_block(const abb_graph *g, const WalkArgs &A, const BlockTier &T, int grid_cap, cudaStream_t st) {
+    auto kern = walk_block_kernel<W, QSM, PAR, META, MINB>;
+    size_t smem = static_cast<size_t>(T.slots) * 4;
+    if (QSM) smem += static_cast<size_t>(T.qcap) * (PAR ? 9 : 5);
+    smem = (smem + 15) & ~static_cast<size_t>(15);
+    static thread_local int occ_cache = -1;   // per instantiation
+    static thread_local size_t smem_cache = 0;
+    if (occ_cache < 0 || smem_cache != smem) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        int occ = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, W * 32, smem));
+        occ_cache = std::max(1, occ); smem_cache = smem;
+    }
+    int grid = g->sm_count * occ_cache;
+    if (grid_cap > 0) grid = std::min(grid, grid_cap);
+    kern<<<static_cast<unsigned>(grid), W * 32, smem, st>>>(A, T);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return ABB_OK;
+}
+
+static int ceil_log2_i64(int64_t n) { int b = 1; while ((1ll << b) < n) b++; return b; }
+
+// Up to five tiers on one stream.  `A` carries spec/io and the first tier's work list (qlist/nq/nq_dev); every later
 // tier reads its work list and count from device memory, so nothing here waits for the GPU.
-//   S1  warp + shared-memory hash/queue            (<= 256 queue entries by default; 512 with ABB_S1_CFG=0)
-//   G1  warp + global bitmap, bounded queue slot   (<= 64K queue entries), 40 warps per SM (ABB_G1_WARPS_PER_SM)
-//   GX  warp + global bitmap, whole-graph slot     (anything)
-// ctl: 12 counters — tier t uses ctl[4t .. 4t+3] = {work cursor, overflow count, fatal flag, -}
-static int enqueue_tiers(abb_graph *g, WalkArgs A, int64_t max_items, unsigned long long *ctl, int32_t *ov1, int32_t *ov2, cudaStream_t st) {
+//   S1  warp  + shared-memory hash/queue           (<= 256 queue entries by default; 512 with ABB_S1_CFG=0)
+//   M   block (8 warps)  + shared-memory hash/queue (<= 4096 entries)                     — walkb.cuh, plain walks only
+//   B   block (32 warps) + 192 KB shared-memory hash, queue in global scratch (<= 36864)  — walkb.cuh, plain walks only
+//   G1  warp  + global bitmap, bounded queue slot  (<= 64K queue entries), 40 warps per SM (ABB_G1_WARPS_PER_SM)
+//   GX  warp  + global bitmap, whole-graph slot    (anything)
+// "plain" = no node/edge budget, no target stop, no recorded edges; the others go S1 -> G1 -> GX.
+// ctl: tier t uses ctl[4t .. 4t+3] = {work cursor, overflow count, fatal flag, -}; a skipped tier's counters stay zero.
+static int enqueue_tiers(abb_graph *g, WalkArgs A, int64_t max_items, unsigned long long *ctl, cudaStream_t st) {
     const uint32_t fl = A.spec.flags;
     const bool par = fl & ABB_WALK_PARENTS;
     const bool meta = A.spec.rel_mask != 0xFFFFFFFFu || (fl & ABB_WALK_TRAVERSABLE_ONLY);
     const bool bud = A.spec.max_nodes >= 0 || A.spec.max_edges >= 0;
-    A.ctl = ctl; A.overflow = ov1;
+    int32_t *ovs[4] = {g->ov1.as<int32_t>(), g->ov2.as<int32_t>(), g->ov3.as<int32_t>(), g->ov4.as<int32_t>()};
+    A.ctl = ctl; A.overflow = ovs[0];
     A.slice_align = g->slice_align;
     if (g->s1_cfg == 1) { if (int rc = launch_smem_variant<512, 256, 8>(g, A, max_items, par, meta, bud, st)) return rc; }
     else if (int rc = launch_smem_variant<S1_H, S1_Q, S1_WARPS>(g, A, max_items, par, meta, bud, st)) return rc;
-    A.qlist = ov1; A.nq = 0; A.nq_dev = ctl + 1; A.ctl = ctl + 4; A.overflow = ov2;
+    int prev = 0;                                   // tier whose overflow list feeds the next launch
+    auto chain = [&](int tier, int32_t *next_ov) {
+        A.qlist = ovs[prev]; A.nq = 0; A.nq_dev = ctl + 4 * prev + 1; A.ctl = ctl + 4 * tier; A.overflow = next_ov;
+    };
+    const int idb = ceil_log2_i64(std::max<int64_t>(g->v.n, 2));
+    const bool plain = !bud && !(fl & (ABB_WALK_TARGET | ABB_WALK_EDGES));
+    if (plain && (g->block_tiers & 1) && idb <= 28) {
+        chain(1, ovs[1]);
+        BlockTier T{static_cast<uint32_t>(g->mid_slots), g->mid_qcap, idb, nullptr, nullptr, nullptr};
+        int rc;
+        if (par && meta) rc = launch_block<8, true, true, true, 3>(g, A, T, 0, st);
+        else if (par) rc = launch_block<8, true, true, false, 3>(g, A, T, 0, st);
+        else if (meta) rc = launch_block<8, true, false, true, 4>(g, A, T, 0, st);
+        else rc = launch_block<8, true, false, false, 4>(g, A, T, 0, st);
+        if (rc) return rc;
+        prev = 1;
+    }
+    if (plain && (g->block_tiers & 2) && idb <= 26) {
+        chain(2, ovs[2]);
+        const size_t words = static_cast<size_t>(g->big_grid) * g->big_qcap;
+        if (int rc = g->b_gq.ensure(words * 4)) return rc;
+        if (par) if (int rc = g->b_gpar.ensure(words * 4)) return rc;
+        if (fl & ABB_WALK_DEPTHS) if (int rc = g->b_gdep.ensure(words * 4)) return rc;
+        BlockTier T{static_cast<uint32_t>(g->big_slots), g->big_qcap, idb, g->b_gq.as<int32_t>(), g->b_gpar.as<int32_t>(), g->b_gdep.as<int32_t>()};
+        int rc = meta ? launch_block<32, false, true, true, 1>(g, A, T, g->big_grid, st) : launch_block<32, false, true, false, 1>(g, A, T, g->big_grid, st);
+        if (rc) return rc;
+        prev = 2;
+    }
+    chain(3, ovs[3]);
     A.g_bitmap = g->g_bitmap.as<uint32_t>(); A.g_queue = g->g_queue.as<int32_t>(); A.g_par = g->g_par.as<int32_t>(); A.g_dep = g->g_dep.as<int32_t>();
     A.g_words = g->g_words; A.g_qcap = g->g_qcap;
     if (int rc = launch_global_variant(A, g->g_slots, g->sm_count, meta, bud, st)) return rc;
-    A.qlist = ov2; A.nq_dev = ctl + 5; A.ctl = ctl + 8; A.overflow = nullptr;
+    prev = 3;
+    chain(4, nullptr);
     A.g_bitmap = g->x_bitmap.as<uint32_t>(); A.g_queue = g->x_queue.as<int32_t>(); A.g_par = g->x_par.as<int32_t>(); A.g_dep = g->x_dep.as<int32_t>();
     A.g_qcap = g->x_qcap;
     return launch_global_variant(A, g->x_slots, g->sm_count, meta, bud, st);
@@ -567,7 +666,7 @@ static int enqueue_dedup_walk(abb_graph *g, const abb_walk_spec *spec, const abb
     C.qlist = nullptr; C.nq = 0; C.nq_dev = cnt;
     C.depth_bias = 1; C.hist_roots = 1;
     C.mem_off = memoff; C.mem_src = g->dd_memsrc.as<int32_t>(); C.mem_state = g->dd_memstate.as<int32_t>();
-    if ((rc = enqueue_tiers(g, C, nq, ctl, g->ov1.as<int32_t>(), g->ov2.as<int32_t>(), st))) return rc;
+    if ((rc = enqueue_tiers(g, C, nq, ctl, st))) return rc;
     dedup_share_kernel<<<static_cast<unsigned>(std::min<int64_t>((nq + 255) / 256, static_cast<int64_t>(g->sm_count) * 8)), 256, 0, st>>>(
         sq, gid, g->dd_memstate.as<int32_t>(), cnt, C.io.q_start, C.io.q_count, C.io.q_maxd, C.io.q_flags, C.io.q_hist, io->q_start, io->q_count, io->q_maxd,
         io->q_flags, (fl & ABB_WALK_HIST) ? io->q_hist : nullptr, indiv, cnt);
@@ -577,7 +676,7 @@ static int enqueue_dedup_walk(abb_graph *g, const abb_walk_spec *spec, const abb
     WalkArgs I{};
     I.g = g->v; I.spec = *spec; I.io = *io;
     I.qlist = indiv; I.nq = 0; I.nq_dev = cnt + 1;
-    return enqueue_tiers(g, I, nq, ctl + 16, g->ov1.as<int32_t>(), g->ov2.as<int32_t>(), st);
+    return enqueue_tiers(g, I, nq, ctl + CTL_SET, st);
 }
 
 static bool dedup_applies(const abb_graph *g, const abb_walk_spec *spec, const abb_walk_io *io) {
@@ -592,14 +691,16 @@ static int enqueue_walk(abb_graph *g, const abb_walk_spec *spec, const abb_walk_
     if (io->n_queries == 0) return ABB_OK;
     if (int rc = g->ov1.ensure(static_cast<size_t>(io->n_queries) * 4)) return rc;
     if (int rc = g->ov2.ensure(static_cast<size_t>(io->n_queries) * 4)) return rc;
-    CUDA_TRY(cudaMemsetAsync(g->ctl.p, 0, 64 * sizeof(unsigned long long), st));
+    if (int rc = g->ov3.ensure(static_cast<size_t>(io->n_queries) * 4)) return rc;
+    if (int rc = g->ov4.ensure(static_cast<size_t>(io->n_queries) * 4)) return rc;
+    CUDA_TRY(cudaMemsetAsync(g->ctl.p, 0, CTL_WORDS * sizeof(unsigned long long), st));
     g->last_walk_queries = io->n_queries;
     g->last_walk_dedup = dedup_applies(g, spec, io);
     if (g->last_walk_dedup) return enqueue_dedup_walk(g, spec, io, st);
     WalkArgs A{};
     A.g = g->v; A.spec = *spec; A.io = *io;
     A.qlist = nullptr; A.nq = io->n_queries; A.nq_dev = nullptr;
-    return enqueue_tiers(g, A, io->n_queries, g->ctl.as<unsigned long long>(), g->ov1.as<int32_t>(), g->ov2.as<int32_t>(), st);
+    return enqueue_tiers(g, A, io->n_queries, g->ctl.as<unsigned long long>(), st);
 }
 
 extern "C" int abb_walk_launch(abb_graph *g, const abb_walk_spec *spec, const abb_walk_io *io, void *stream) {
@@ -643,6 +744,17 @@ extern "C" int abb_last_walk_stats(abb_graph *g, int64_t *out4) {
         CUDA_TRY(cudaMemcpy(c, g->dd_cnt.p, sizeof c, cudaMemcpyDeviceToHost));
         out4[1] = static_cast<int64_t>(c[0]); out4[2] = static_cast<int64_t>(c[1]); out4[3] = static_cast<int64_t>(c[2]);
     }
+    return ABB_OK;
+}
+
+extern "C" int abb_last_walk_tier_counts(abb_graph *g, int64_t *out8) {
+    if (!g || !out8) return fail(ABB_ERR_ARG, "null argument");
+    DeviceGuard dg(g->device);
+    std::lock_guard<std::mutex> lk(g->mu);
+    unsigned long long c[CTL_WORDS];
+    CUDA_TRY(cudaMemcpy(c, g->ctl.p, sizeof c, cudaMemcpyDeviceToHost));
+    for (int set = 0; set < 2; set++)
+        for (int t = 0; t < 4; t++) out8[set * 4 + t] = static_cast<int64_t>(c[set * CTL_SET + 4 * t + 1]);
     return ABB_OK;
 }
 
@@ -690,7 +802,7 @@ extern "C" int64_t abb_walk_result_d2h_bytes(const abb_walk_result *r) { return 
 // straight into that pinned host block (UVA), so the PCIe transfer of the largest output overlaps the traversal
 // instead of following it; if the estimate turns out too small the walk is re-run into a device arena.
 static int walk_device_stage(abb_graph *g, const abb_walk_spec *spec, const int32_t *roots, const int64_t *root_off, const int32_t *targets,
-                             int64_t nq, abb_walk_io *io_out, unsigned long long totals[3], int64_t *h2d, HostBlock *direct_nodes = nullptr) {
+                             int64_t nq, abb_walk_io *io_out, unsigned long long (&totals)[3], int64_t *h2d, HostBlock *direct_nodes = nullptr) {
     cudaStream_t st = g->stream;
     const uint32_t fl = spec->flags;
     const int64_t n_roots = root_off ? root_off[nq] : nq;
@@ -744,8 +856,8 @@ static int walk_device_stage(abb_graph *g, const abb_walk_spec *spec, const int3
         CUDA_TRY(cudaMemcpyAsync(totals, g->d_totals.p, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
         unsigned long long fatal = 0, fatal2 = 0;
-        CUDA_TRY(cudaMemcpy(&fatal, g->ctl.as<unsigned long long>() + 10, sizeof fatal, cudaMemcpyDeviceToHost));
-        CUDA_TRY(cudaMemcpy(&fatal2, g->ctl.as<unsigned long long>() + 26, sizeof fatal2, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(&fatal, g->ctl.as<unsigned long long>() + CTL_FATAL, sizeof fatal, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(&fatal2, g->ctl.as<unsigned long long>() + CTL_SET + CTL_FATAL, sizeof fatal2, cudaMemcpyDeviceToHost));
         if (fatal || fatal2) return fail(ABB_ERR_CAPACITY, "a traversal outgrew the global scratch tier (more than n_nodes+4096 queue entries)");
         *io_out = io;
         const bool fits = static_cast<int64_t>(totals[0]) <= node_cap && (!(fl & ABB_WALK_EDGES) || static_cast<int64_t>(totals[1]) <= edge_cap);

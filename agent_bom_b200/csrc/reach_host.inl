@@ -81,7 +81,7 @@ extern "C" int abb_dependency_reach_host(abb_graph *g, const int32_t *agents, in
 
     // ---- pass 1: BFS distances from every agent, packages only (dependency_reach.py:121-130)
     abb_walk_spec spec = abb_spec_distances_along(rel_mask, 1u << ET_PACKAGE);
-    abb_walk_io io{}; unsigned long long totals[2] = {0, 0}; int64_t h2d = 0;
+    abb_walk_io io{}; unsigned long long totals[3] = {0, 0, 0}; int64_t h2d = 0;
     if (int rc = walk_device_stage(g, &spec, agents, nullptr, nullptr, n_agents, &io, totals, &h2d)) return rc;
     const int64_t T = static_cast<int64_t>(totals[0]);
 
@@ -110,7 +110,8 @@ extern "C" int abb_dependency_reach_host(abb_graph *g, const int32_t *agents, in
     // ---- host: package / vulnerability node lists in node order
     std::vector<uint8_t> ntype(static_cast<size_t>(n));
     if (n) CUDA_TRY(cudaMemcpy(ntype.data(), g->v.ntype, static_cast<size_t>(n), cudaMemcpyDeviceToHost));
-    abb_reach_result *r = new abb_reach_result();
+    std::unique_ptr<abb_reach_result> r_owner(new abb_reach_result());   // freed on every early return
+    abb_reach_result *r = r_owner.get();
     for (int64_t u = 0; u < n; u++) {
         if (ntype[u] == ET_PACKAGE) r->pkg_ids.push_back(static_cast<int32_t>(u));
         else if (ntype[u] == ET_VULN) r->vuln_ids.push_back(static_cast<int32_t>(u));
@@ -119,30 +120,30 @@ extern "C" int abb_dependency_reach_host(abb_graph *g, const int32_t *agents, in
 
     // ---- pass 2b: vulnerability -> attached packages (unique, sorted by id string)  (:201-220)
     Tmp d_vulns, vcounts, voff;
-    if (int rc = d_vulns.alloc(static_cast<size_t>(nv + 1) * 4)) { delete r; return rc; }
-    if (int rc = vcounts.alloc(static_cast<size_t>(nv + 2) * 8)) { delete r; return rc; }
-    if (int rc = voff.alloc(static_cast<size_t>(nv + 2) * 8)) { delete r; return rc; }
+    if (int rc = d_vulns.alloc(static_cast<size_t>(nv + 1) * 4)) return rc;
+    if (int rc = vcounts.alloc(static_cast<size_t>(nv + 2) * 8)) return rc;
+    if (int rc = voff.alloc(static_cast<size_t>(nv + 2) * 8)) return rc;
     CUDA_TRY(cudaMemsetAsync(vcounts.p, 0, static_cast<size_t>(nv + 2) * 8, st));
     if (nv) CUDA_TRY(cudaMemcpyAsync(d_vulns.p, r->vuln_ids.data(), static_cast<size_t>(nv) * 4, cudaMemcpyHostToDevice, st));
     if (nv) { reach_vuln_pkgs_kernel<false><<<nblk(nv, 128), 128, 0, st>>>(g->v, nv, d_vulns.as<int32_t>(), vuln_pkg_mask, nullptr, vcounts.as<int64_t>(), nullptr, nullptr); g_launches++; }
-    if (int rc = exclusive_scan_i64(st, vcounts.as<int64_t>(), voff.as<int64_t>(), nv + 1)) { delete r; return rc; }
+    if (int rc = exclusive_scan_i64(st, vcounts.as<int64_t>(), voff.as<int64_t>(), nv + 1)) return rc;
     int64_t P0 = 0;
     CUDA_TRY(cudaMemcpy(&P0, voff.as<int64_t>() + nv, 8, cudaMemcpyDeviceToHost));
     Tmp pk, pv, pk2, pv2;
-    if (int rc = pk.alloc(static_cast<size_t>(P0) * 8)) { delete r; return rc; }
-    if (int rc = pv.alloc(static_cast<size_t>(P0) * 4)) { delete r; return rc; }
-    if (int rc = pk2.alloc(static_cast<size_t>(P0) * 8)) { delete r; return rc; }
-    if (int rc = pv2.alloc(static_cast<size_t>(P0) * 4)) { delete r; return rc; }
+    if (int rc = pk.alloc(static_cast<size_t>(P0) * 8)) return rc;
+    if (int rc = pv.alloc(static_cast<size_t>(P0) * 4)) return rc;
+    if (int rc = pk2.alloc(static_cast<size_t>(P0) * 8)) return rc;
+    if (int rc = pv2.alloc(static_cast<size_t>(P0) * 4)) return rc;
     if (nv) { reach_vuln_pkgs_kernel<true><<<nblk(nv, 128), 128, 0, st>>>(g->v, nv, d_vulns.as<int32_t>(), vuln_pkg_mask, voff.as<int64_t>(), nullptr, pk.as<unsigned long long>(), pv.as<int32_t>()); g_launches++; }
     int64_t P = 0;
-    if (int rc = sort_unique_pairs(st, pk.as<unsigned long long>(), pv.as<int32_t>(), pk2.as<unsigned long long>(), pv2.as<int32_t>(), P0, &P, true)) { delete r; return rc; }
+    if (int rc = sort_unique_pairs(st, pk.as<unsigned long long>(), pv.as<int32_t>(), pk2.as<unsigned long long>(), pv2.as<int32_t>(), P0, &P, true)) return rc;
     // per-vulnerability package counts -> vuln_poff
     Tmp gcnt, goff;
-    if (int rc = gcnt.alloc(static_cast<size_t>(nv + 2) * 8)) { delete r; return rc; }
-    if (int rc = goff.alloc(static_cast<size_t>(nv + 2) * 8)) { delete r; return rc; }
+    if (int rc = gcnt.alloc(static_cast<size_t>(nv + 2) * 8)) return rc;
+    if (int rc = goff.alloc(static_cast<size_t>(nv + 2) * 8)) return rc;
     CUDA_TRY(cudaMemsetAsync(gcnt.p, 0, static_cast<size_t>(nv + 2) * 8, st));
     if (P) { reach_group_counts_kernel<<<nblk(P, 256), 256, 0, st>>>(P, pk.as<unsigned long long>(), gcnt.as<unsigned long long>()); g_launches++; }
-    if (int rc = exclusive_scan_i64(st, gcnt.as<int64_t>(), goff.as<int64_t>(), nv + 1)) { delete r; return rc; }
+    if (int rc = exclusive_scan_i64(st, gcnt.as<int64_t>(), goff.as<int64_t>(), nv + 1)) return rc;
     r->vuln_poff.resize(static_cast<size_t>(nv) + 1);
     CUDA_TRY(cudaMemcpy(r->vuln_poff.data(), goff.p, static_cast<size_t>(nv + 1) * 8, cudaMemcpyDeviceToHost));
     r->vuln_pkgs.resize(static_cast<size_t>(P));
@@ -150,26 +151,26 @@ extern "C" int abb_dependency_reach_host(abb_graph *g, const int32_t *agents, in
 
     // ---- pass 2c: vulnerability -> union of agents of its reachable packages, min of their mins  (:147-164)
     Tmp pcounts, poff, vmin;
-    if (int rc = pcounts.alloc(static_cast<size_t>(P + 2) * 8)) { delete r; return rc; }
-    if (int rc = poff.alloc(static_cast<size_t>(P + 2) * 8)) { delete r; return rc; }
-    if (int rc = vmin.alloc(static_cast<size_t>(nv + 1) * 4)) { delete r; return rc; }
+    if (int rc = pcounts.alloc(static_cast<size_t>(P + 2) * 8)) return rc;
+    if (int rc = poff.alloc(static_cast<size_t>(P + 2) * 8)) return rc;
+    if (int rc = vmin.alloc(static_cast<size_t>(nv + 1) * 4)) return rc;
     CUDA_TRY(cudaMemsetAsync(pcounts.p, 0, static_cast<size_t>(P + 2) * 8, st));
     fill_i32_kernel<<<nblk(nv, 256), 256, 0, st>>>(vmin.as<int32_t>(), nv, 0x7FFFFFFF); g_launches++;
     if (P) { reach_pair_counts_kernel<<<nblk(P, 256), 256, 0, st>>>(P, pk.as<unsigned long long>(), pv.as<int32_t>(), cnt.as<unsigned long long>(), minhop.as<int32_t>(), pcounts.as<int64_t>(), vmin.as<int32_t>()); g_launches++; }
-    if (int rc = exclusive_scan_i64(st, pcounts.as<int64_t>(), poff.as<int64_t>(), P + 1)) { delete r; return rc; }
+    if (int rc = exclusive_scan_i64(st, pcounts.as<int64_t>(), poff.as<int64_t>(), P + 1)) return rc;
     int64_t A0 = 0;
     CUDA_TRY(cudaMemcpy(&A0, poff.as<int64_t>() + P, 8, cudaMemcpyDeviceToHost));
     Tmp ak, av, ak2, av2;
-    if (int rc = ak.alloc(static_cast<size_t>(A0) * 8)) { delete r; return rc; }
-    if (int rc = av.alloc(static_cast<size_t>(A0) * 4)) { delete r; return rc; }
-    if (int rc = ak2.alloc(static_cast<size_t>(A0) * 8)) { delete r; return rc; }
-    if (int rc = av2.alloc(static_cast<size_t>(A0) * 4)) { delete r; return rc; }
+    if (int rc = ak.alloc(static_cast<size_t>(A0) * 8)) return rc;
+    if (int rc = av.alloc(static_cast<size_t>(A0) * 4)) return rc;
+    if (int rc = ak2.alloc(static_cast<size_t>(A0) * 8)) return rc;
+    if (int rc = av2.alloc(static_cast<size_t>(A0) * 4)) return rc;
     if (P) { reach_pair_fill_kernel<<<nblk(P, 8), 256, 0, st>>>(P, pk.as<unsigned long long>(), pv.as<int32_t>(), poff.as<int64_t>(), noff.as<int64_t>(), vals.as<int32_t>(), g->v.rank, ak.as<unsigned long long>(), av.as<int32_t>()); g_launches++; }
     int64_t AU = 0;
-    if (int rc = sort_unique_pairs(st, ak.as<unsigned long long>(), av.as<int32_t>(), ak2.as<unsigned long long>(), av2.as<int32_t>(), A0, &AU, true)) { delete r; return rc; }
+    if (int rc = sort_unique_pairs(st, ak.as<unsigned long long>(), av.as<int32_t>(), ak2.as<unsigned long long>(), av2.as<int32_t>(), A0, &AU, true)) return rc;
     CUDA_TRY(cudaMemsetAsync(gcnt.p, 0, static_cast<size_t>(nv + 2) * 8, st));
     if (AU) { reach_group_counts_kernel<<<nblk(AU, 256), 256, 0, st>>>(AU, ak.as<unsigned long long>(), gcnt.as<unsigned long long>()); g_launches++; }
-    if (int rc = exclusive_scan_i64(st, gcnt.as<int64_t>(), goff.as<int64_t>(), nv + 1)) { delete r; return rc; }
+    if (int rc = exclusive_scan_i64(st, gcnt.as<int64_t>(), goff.as<int64_t>(), nv + 1)) return rc;
     minhop_finalize_kernel<<<nblk(n, 256), 256, 0, st>>>(minhop.as<int32_t>(), n); g_launches++;
     minhop_finalize_kernel<<<nblk(nv, 256), 256, 0, st>>>(vmin.as<int32_t>(), nv); g_launches++;
     CUDA_TRY(cudaGetLastError());
@@ -192,6 +193,6 @@ extern "C" int abb_dependency_reach_host(abb_graph *g, const int32_t *agents, in
     r->pkg_off.resize(np + 1); r->pkg_minhop.resize(np);
     for (size_t i = 0; i < np; i++) { r->pkg_off[i] = h_noff[r->pkg_ids[i]]; r->pkg_minhop[i] = h_min[r->pkg_ids[i]]; }
     r->pkg_off[np] = T;   // only package nodes were emitted, so the sorted pair array is exactly their concatenation
-    *out = r;
+    *out = r_owner.release();
     return ABB_OK;
 }

@@ -125,7 +125,8 @@ struct GlobalStore {
     __device__ void init(int) {}
     __device__ __forceinline__ int qcap() const { return cap; }
     __device__ __forceinline__ int max_level() const { return 0x7FFFFFF0; }
-    __device__ __forceinline__ bool contains(int32_t k) const { return (bits[k >> 5] >> (k & 31)) & 1u; }
+    // read through L2 (ld.cg): the bits are set by L2 atomics, an L1 line could be stale
+    __device__ __forceinline__ bool contains(int32_t k) const { return (__ldcg(bits + (k >> 5)) >> (k & 31)) & 1u; }
     __device__ __forceinline__ bool test_and_set(int32_t k, uint32_t &t) {
         t = 0;
         uint32_t bit = 1u << (k & 31);
@@ -230,6 +231,72 @@ __device__ __forceinline__ bool type_emitted(uint32_t emit_types, uint8_t t) {
     return (emit_types >> (t < 31 ? t : 31)) & 1u;
 }
 
+
+// ---------------------------------------------------------------- row mode
+// Lean expansion of ONE frontier node's row(s): candidates are consumed 32 at a time in row order (forward row, then
+// reverse row), which is exactly the reference's scan order for that node, with no flattening scan / search.  The
+// visited set is PROBED first (plain loads); the ordered insert/append machinery runs only for chunks that hold an
+// unvisited candidate — on clique-shaped inventories >90 % of all scanned entries are revisits (80 agents sharing a
+// credential each list the other 79), so the common chunk costs one coalesced load, one hash and one probe.
+struct RowCand { int32_t nbr; uint32_t meta; uint32_t pos; bool fwd; bool active; };
+
+template <bool NEED_META>
+__device__ __forceinline__ RowCand row_load(const GraphView &g, uint32_t sF, uint32_t dF, uint32_t sR, uint32_t tot, uint32_t k) {
+    RowCand c; c.active = k < tot; c.nbr = 0; c.meta = ABB_META_TRAVERSABLE; c.pos = 0; c.fwd = true;
+    if (c.active) {
+        if (k < dF) { c.pos = sF + k; c.nbr = __ldg(g.fnbr + c.pos); if (NEED_META) c.meta = __ldg(g.fmeta + c.pos); }
+        else { c.fwd = false; c.pos = sR + (k - dF); c.nbr = __ldg(g.rnbr + c.pos); if (NEED_META) c.meta = __ldg(g.rmeta + c.pos); }
+    }
+    return c;
+}
+
+// Returns false when the store overflowed (the caller re-queues the query; the store has been cleared).
+template <class Store, bool NEED_META, class idx_t>
+__device__ __forceinline__ bool expand_row(const WalkArgs &A, Store &st, uint32_t sF, uint32_t dF, uint32_t sR, uint32_t tot, int32_t parent_pos, int depth1,
+                                           int lane, idx_t &tail, long long &rec_edges) {
+    const GraphView &g = A.g;
+    const abb_walk_spec &sp = A.spec;
+    const uint32_t fl = sp.flags;
+    // two chunks in flight ahead of the one being probed
+    RowCand n1 = row_load<NEED_META>(g, sF, dF, sR, tot, lane);
+    RowCand n2 = row_load<NEED_META>(g, sF, dF, sR, tot, 32 + lane);
+    for (uint32_t c0 = 0; c0 < tot; c0 += 32) {
+        const RowCand c = n1;
+        n1 = n2;
+        n2 = row_load<NEED_META>(g, sF, dF, sR, tot, c0 + 64 + lane);
+        bool pass = c.active;
+        if (NEED_META) pass = pass && ((sp.rel_mask >> (c.meta & ABB_META_REL_MASK)) & 1u) && (!(fl & ABB_WALK_TRAVERSABLE_ONLY) || (c.meta & ABB_META_TRAVERSABLE));
+        if (fl & ABB_WALK_EDGES) rec_edges += __popc(__ballot_sync(FULL, pass));
+        const bool unv = pass && !st.contains(c.nbr);
+        if (__ballot_sync(FULL, unv) == 0u) continue;
+        // rare path: some candidate of this chunk is new.  The first occurrence of a neighbour inside the chunk speaks for it:
+        // FIRST_PAIR when the chunk lies in one unfiltered row (an earlier occurrence in an earlier chunk would already be visited).
+        bool leader;
+        if (!NEED_META && sp.direction != ABB_DIR_BOTH) {
+            const uint32_t m = unv ? static_cast<uint32_t>(__ldg((c.fwd ? g.fmeta : g.rmeta) + c.pos)) : 0u;
+            leader = unv && (m & ABB_META_FIRST_PAIR);
+        } else {
+            const unsigned mm = __match_any_sync(FULL, unv ? c.nbr : (-2 - lane));
+            leader = unv && (__ffs(mm) - 1) == lane;
+        }
+        uint32_t tok = NO_TOK;
+        const bool isnew = leader && st.test_and_set(c.nbr, tok);
+        const unsigned nm = __ballot_sync(FULL, isnew);
+        const int cnt = __popc(nm);
+        if (cnt) {
+            if (tail + cnt > st.qcap()) {
+                if (isnew) st.unset(c.nbr, tok);
+                st.clear(tail, lane);
+                return false;
+            }
+            if (isnew) st.put(tail + __popc(nm & lanemask_lt(lane)), c.nbr, parent_pos, tok, depth1);
+            tail += cnt;
+        }
+        __syncwarp();
+    }
+    return true;
+}
+
 // ---------------------------------------------------------------- one query
 // Returns false when the query outgrew the store (caller re-queues it for the next tier).
 template <class Store, bool NEED_META, bool BUDGET>
@@ -304,7 +371,10 @@ __device__ bool walk_one(const WalkArgs &A, Store &st, int64_t q, int lane, uint
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) cand += __shfl_xor_sync(FULL, cand, o);
-            if (cand > 3ull * static_cast<unsigned long long>(st.qcap() - tail) + 64ull) { st.clear(tail, lane); return false; }
+            // (shared-memory tier: only a gross excess counts — on clique-shaped graphs most candidates are revisits, and a wrong
+            //  guess costs at most one queue-full of discoveries there)
+            const unsigned long long factor = Store::kGlobal ? 3ull : 64ull;
+            if (cand > factor * static_cast<unsigned long long>(st.qcap() - tail) + 64ull) { st.clear(tail, lane); return false; }
         }
         for (idx_t base = lvl_begin; base < lvl_end && !stop; base += 32) {
             const bool single = (lvl_end - base) == 1;
@@ -322,6 +392,23 @@ __device__ bool walk_one(const WalkArgs &A, Store &st, int64_t q, int lane, uint
                 f = load_frontier(g, sp.direction, u, fvalid);
             }
             exp_end = (base + 32 < lvl_end) ? base + 32 : lvl_end;
+            const uint32_t nrows = static_cast<uint32_t>(exp_end - base);
+            if (!BUDGET && !(fl & ABB_WALK_TARGET) && (single || f.total >= 4u * nrows)) {
+                // row mode (long rows): one frontier node after the other, in queue order
+                if (single) {
+                    if (!expand_row<Store, NEED_META, idx_t>(A, st, f.sF, f.dF, f.sR, f.total, static_cast<int32_t>(base), depth + 1, lane, tail, rec_edges)) return false;
+                } else {
+                    const uint32_t incl = f.excl, tot_all = f.total;
+                    for (uint32_t j = 0; j < nrows; j++) {
+                        const uint32_t sF = __shfl_sync(FULL, f.sF, j), dF = __shfl_sync(FULL, f.dF, j), sR = __shfl_sync(FULL, f.sR, j);
+                        const uint32_t e0 = __shfl_sync(FULL, incl, j), e1 = (j + 1 < 32) ? __shfl_sync(FULL, incl, (j + 1) & 31) : tot_all;
+                        const uint32_t tot = ((j + 1 < 32) ? e1 : tot_all) - e0;
+                        if (tot == 0) continue;
+                        if (!expand_row<Store, NEED_META, idx_t>(A, st, sF, dF, sR, tot, static_cast<int32_t>(base + j), depth + 1, lane, tail, rec_edges)) return false;
+                    }
+                }
+                continue;
+            }
             // software pipeline: the next chunk's neighbour loads are in flight while this chunk's visited-set round trip resolves
             Cand nxt;
             if (f.total) nxt = single ? fetch_single<true, false>(g, f.sF, f.dF, f.sR, f.total, lane) : fetch_cand<true, false>(g, f, lane);
@@ -369,7 +456,8 @@ __device__ bool walk_one(const WalkArgs &A, Store &st, int64_t q, int lane, uint
                     // a non-leader duplicate of a denied neighbour is denied too (still unvisited, budget still full)
                     if (allowed) isnew = st.test_and_set(c.nbr, tok);
                 } else if (leader) {
-                    isnew = st.test_and_set(c.nbr, tok);
+                    // global tier: a revisit is answered by a plain L2 load instead of an atomic round trip
+                    if (!Store::kGlobal || !st.contains(c.nbr)) isnew = st.test_and_set(c.nbr, tok);
                 }
                 unsigned nm = __ballot_sync(FULL, isnew);
                 int cnt = __popc(nm);
@@ -496,7 +584,7 @@ __device__ __forceinline__ int64_t next_chunk(unsigned long long *ctl, int lane)
 
 // ---------------------------------------------------------------- kernels
 template <int H, int Q, bool PAR, bool NEED_META, bool BUDGET, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) walk_smem_kernel(const WalkArgs A) {
+__global__ void __launch_bounds__(WARPS * 32, 5) walk_smem_kernel(const WalkArgs A) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ uint32_t s_hist[WARPS][ABB_N_ENTITY_TYPES];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -153,6 +153,13 @@ class DeviceGraph:
         """Toggle root-frontier de-duplication of single-source batches (results are identical either way)."""
         _lib.check(_lib.load().abb_graph_set_dedup(self.handle, int(bool(enabled))))
 
+    def set_option(self, name: str, value: int) -> None:
+        """Tuning / test switch of the handle (``abb_graph_set_option``): block_tiers, mid_qcap, big_qcap, dedup, zero_copy."""
+        _lib.check(_lib.load().abb_graph_set_option(self.handle, name.encode(), int(value)))
+
+    def get_option(self, name: str) -> int:
+        return int(_lib.load().abb_graph_get_option(self.handle, name.encode()))
+
     @property
     def nbytes(self) -> int:
         return int(_lib.load().abb_graph_bytes(self.handle))
@@ -352,6 +359,13 @@ class DeviceGraph:
         out = (C.c_int64 * 4)()
         _lib.check(_lib.load().abb_last_walk_stats(self.handle, out))
         return {"queries": int(out[0]), "groups": int(out[1]), "individual": int(out[2]), "eligible": int(out[3])}
+
+    def last_walk_tier_counts(self) -> dict:
+        """Queries each storage tier of the most recent walk handed to the next tier (first pass / individual pass)."""
+        out = (C.c_int64 * 8)()
+        _lib.check(_lib.load().abb_last_walk_tier_counts(self.handle, out))
+        names = ("s1", "mid", "big", "g1")
+        return {"first": dict(zip(names, [int(x) for x in out[0:4]])), "individual": dict(zip(names, [int(x) for x in out[4:8]]))}
 
     def last_paths_ms(self) -> float:
         return float(_lib.load().abb_last_paths_ms(self.handle))

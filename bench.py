@@ -311,6 +311,8 @@ def main() -> int:
     torch.cuda.synchronize()
     abdist.barrier(info)
     walk_stats = dg.last_walk_stats()
+    tier_counts = dg.last_walk_tier_counts()
+    log(f"[bench] rank {info.rank}: tier hand-offs of the last walk: {tier_counts}")
     launches = lib.abb_launch_count() - launches0
     dev_ms = start.elapsed_time(end)
     walk_ms = sum(a.elapsed_time(b) for a, b in walk_events)
