@@ -7,6 +7,7 @@ no CPU fallback for the traversal path.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import threading
 from pathlib import Path
 
@@ -192,8 +193,13 @@ def load(build_if_missing: bool = True):
                 _build.build()
             except Exception as exc:  # nvcc missing / compile error
                 raise EngineUnavailable(f"cannot build {LIB_PATH.name}: {exc}") from exc
+        path = LIB_PATH
+        if os.environ.get("ABB_LIB"):      # experiment build (python -m agent_bom_b200.build <variant> <defines…>), A/B measurements only
+            path = PKG / os.environ["ABB_LIB"]
+            if not path.exists():
+                raise EngineUnavailable(f"ABB_LIB={os.environ['ABB_LIB']}: {path} does not exist")
         try:
-            lib = C.CDLL(str(LIB_PATH))
+            lib = C.CDLL(str(path))
         except OSError as exc:
             raise EngineUnavailable(f"cannot load {LIB_PATH}: {exc}") from exc
         for name, (restype, argtypes) in EXPORTS.items():

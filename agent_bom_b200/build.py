@@ -41,17 +41,21 @@ def is_stale() -> bool:
     return any(d.stat().st_mtime > t for d in DEPS if d.exists())
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    if not force and not is_stale():
+def build(force: bool = False, verbose: bool = False, variant: str = "", defines: tuple = ()) -> Path:
+    """Default: libabb200.so.  `variant` + `defines` build an experiment library next to it (libabb200_<variant>.so with the given
+    -D flags; loaded through the ABB_LIB environment variable) — used for in-run A/B measurements, never by the product path."""
+    out = LIB if not variant else PKG / f"libabb200_{variant}.so"
+    if not variant and not force and not is_stale():
         return LIB
-    cmd = [find_nvcc(), *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", str(LIB), *map(str, SOURCES)]
+    cmd = [find_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], *(["-Xptxas", "-v"] if verbose else []), "-o", str(out), *map(str, SOURCES)]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or proc.returncode:
         sys.stderr.write(proc.stdout + proc.stderr)
     if proc.returncode:
         raise RuntimeError(f"nvcc failed ({proc.returncode}): {' '.join(cmd)}")
-    return LIB
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, variant=args[0] if args else "", defines=tuple(args[1:])))

@@ -190,6 +190,7 @@ struct abb_graph {
     int block_tiers = 3;              // bit 0: mid tier, bit 1: big tier (ABB_BLOCK_TIERS / abb_graph_set_option)
     int mid_slots = 8192, mid_qcap = 4096, big_slots = 49152, big_qcap = 36864;
     int big_grid = 0;
+    int mid_warps = 8;                // ABB_MID_WARPS=4: 4-warp mid blocks
     DevBuf b_gq, b_gpar, b_gdep;
     // tier G1: many per-warp slots (bitmap over all nodes + a bounded queue); tier GX: a few slots that can hold a whole-graph walk
     DevBuf g_bitmap, g_queue, g_par, g_dep;
@@ -205,7 +206,7 @@ struct abb_graph {
     bool zero_copy = true;      // host-API walks write the node arena straight into pinned host memory when its size is known
     int64_t last_walk_queries = 0;
     bool last_walk_dedup = false;
-    int s1_cfg = 1;   // 1: 512-slot hash / 256-entry queue (more resident warps, earlier hand-off to G1; measured best), 0: 1024/512
+    int s1_minb = 5;
     DevBuf identity_rank;
     // host-API staging
     DevBuf d_roots, d_root_off, d_targets, d_qstart, d_qcount, d_qmaxd, d_qflags, d_qestart, d_qecount, d_qhist;
@@ -269,7 +270,8 @@ static int graph_finish_init(abb_graph *g) {
     if (const char *e = getenv("ABB_DEDUP")) g->dedup_enabled = atoi(e) != 0;
     if (const char *e = getenv("ABB_BLOCK_TIERS")) g->block_tiers = atoi(e) & 3;
     g->big_grid = g->sm_count;
-    if (const char *e = getenv("ABB_S1_CFG")) g->s1_cfg = atoi(e);
+    if (const char *e = getenv("ABB_MID_WARPS")) g->mid_warps = atoi(e) == 4 ? 4 : 8;
+    if (const char *e = getenv("ABB_S1_MINB")) g->s1_minb = atoi(e) == 4 ? 4 : 5;
     if (const char *e = getenv("ABB_ZEROCOPY")) g->zero_copy = atoi(e) != 0;
     if (const char *e = getenv("ABB_ALIGN_DIRECT")) g->align_direct = atoi(e) != 0;
     if (!g->v.rank) {
@@ -395,6 +397,7 @@ extern "C" int64_t abb_graph_get_option(const abb_graph *g, const char *name) {
 extern "C" void abb_graph_free(abb_graph *g) {
     if (!g) return;
     DeviceGuard dg(g->device);
+    { std::lock_guard<std::mutex> lk(g->mu); }      // a host-API call still inside the library finishes before the teardown starts
     if (g->stream) { cudaStreamSynchronize(g->stream); cudaStreamDestroy(g->stream); }
     if (g->copy_stream) { cudaStreamSynchronize(g->copy_stream); cudaStreamDestroy(g->copy_stream); }
     if (g->ev_copy) cudaEventDestroy(g->ev_copy);
@@ -461,11 +464,11 @@ extern "C" abb_walk_spec abb_spec_distances_along(uint32_t rel_mask, uint32_t em
 }
 
 // ------------------------------------------------------------------ walk dispatch
-constexpr int S1_H = 1024, S1_Q = 512, S1_WARPS = 8;
+constexpr int S1_H = 1024, S1_Q = 256, S1_WARPS = 8;      // 256 four-slot buckets, 256-entry queue per warp (5.4 KB): 40 warps per SM
 
-template <int H, int Q, int WARPS, bool PAR, bool META, bool BUD>
+template <int H, int Q, int WARPS, bool PAR, bool META, bool BUD, int MINB>
 static int launch_smem(const abb_graph *g, const WalkArgs &A, int64_t max_items, cudaStream_t st) {
-    auto kern = walk_smem_kernel<H, Q, PAR, META, BUD, WARPS>;
+    auto kern = walk_smem_kernel<H, Q, PAR, META, BUD, WARPS, MINB>;
     constexpr int stride = (SmemStore<H, Q, PAR>::kBytes + 15) & ~15;
     const int smem = stride * WARPS;
     static thread_local int occ_cache = -1;  // per instantiation
@@ -486,7 +489,8 @@ static int launch_smem(const abb_graph *g, const WalkArgs &A, int64_t max_items,
 
 template <int H, int Q, int WARPS>
 static int launch_smem_variant(const abb_graph *g, const WalkArgs &A, int64_t max_items, bool par, bool meta, bool bud, cudaStream_t st) {
-#define V(P, M, B) if (par == P && meta == M && bud == B) return launch_smem<H, Q, WARPS, P, M, B>(g, A, max_items, st)
+    // MINB: resident blocks the register allocation aims for — 5 (48 registers, 40 warps/SM) or 4 (64 registers, 32 warps/SM; ABB_S1_MINB=4)
+#define V(P, M, B) if (par == P && meta == M && bud == B) return g->s1_minb == 4 ? launch_smem<H, Q, WARPS, P, M, B, 4>(g, A, max_items, st) : launch_smem<H, Q, WARPS, P, M, B, 5>(g, A, max_items, st)
     V(false, false, false); V(false, false, true); V(false, true, false); V(false, true, true);
     V(true, false, false); V(true, false, true); V(true, true, false); V(true, true, true);
 #undef V
@@ -536,7 +540,7 @@ static int ceil_log2_i64(int64_t n) { int b = 1; while ((1ll << b) < n) b++; ret
 
 // Up to five tiers on one stream.  `A` carries spec/io and the first tier's work list (qlist/nq/nq_dev); every later
 // tier reads its work list and count from device memory, so nothing here waits for the GPU.
-//   S1  warp  + shared-memory hash/queue           (<= 256 queue entries by default; 512 with ABB_S1_CFG=0)
+//   S1  warp  + shared-memory hash/queue           (<= 256 queue entries)
 //   M   block (8 warps)  + shared-memory hash/queue (<= 4096 entries)                     — walkb.cuh, plain walks only
 //   B   block (32 warps) + 192 KB shared-memory hash, queue in global scratch (<= 36864)  — walkb.cuh, plain walks only
 //   G1  warp  + global bitmap, bounded queue slot  (<= 64K queue entries), 40 warps per SM (ABB_G1_WARPS_PER_SM)
@@ -551,8 +555,7 @@ static int enqueue_tiers(abb_graph *g, WalkArgs A, int64_t max_items, unsigned l
     int32_t *ovs[4] = {g->ov1.as<int32_t>(), g->ov2.as<int32_t>(), g->ov3.as<int32_t>(), g->ov4.as<int32_t>()};
     A.ctl = ctl; A.overflow = ovs[0];
     A.slice_align = g->slice_align;
-    if (g->s1_cfg == 1) { if (int rc = launch_smem_variant<512, 256, 8>(g, A, max_items, par, meta, bud, st)) return rc; }
-    else if (int rc = launch_smem_variant<S1_H, S1_Q, S1_WARPS>(g, A, max_items, par, meta, bud, st)) return rc;
+    if (int rc = launch_smem_variant<S1_H, S1_Q, S1_WARPS>(g, A, max_items, par, meta, bud, st)) return rc;
     int prev = 0;                                   // tier whose overflow list feeds the next launch
     auto chain = [&](int tier, int32_t *next_ov) {
         A.qlist = ovs[prev]; A.nq = 0; A.nq_dev = ctl + 4 * prev + 1; A.ctl = ctl + 4 * tier; A.overflow = next_ov;
@@ -563,7 +566,13 @@ static int enqueue_tiers(abb_graph *g, WalkArgs A, int64_t max_items, unsigned l
         chain(1, ovs[1]);
         BlockTier T{static_cast<uint32_t>(g->mid_slots), g->mid_qcap, idb, nullptr, nullptr, nullptr};
         int rc;
-        if (par && meta) rc = launch_block<8, true, true, true, 3>(g, A, T, 0, st);
+        if (g->mid_warps == 4) {               // 4-warp blocks: half the table / queue, twice the walks in flight per SM
+            T.slots = static_cast<uint32_t>(std::min(g->mid_slots, 4096)); T.qcap = std::min(g->mid_qcap, 2048);
+            if (par && meta) rc = launch_block<4, true, true, true, 6>(g, A, T, 0, st);
+            else if (par) rc = launch_block<4, true, true, false, 6>(g, A, T, 0, st);
+            else if (meta) rc = launch_block<4, true, false, true, 8>(g, A, T, 0, st);
+            else rc = launch_block<4, true, false, false, 8>(g, A, T, 0, st);
+        } else if (par && meta) rc = launch_block<8, true, true, true, 3>(g, A, T, 0, st);
         else if (par) rc = launch_block<8, true, true, false, 3>(g, A, T, 0, st);
         else if (meta) rc = launch_block<8, true, false, true, 4>(g, A, T, 0, st);
         else rc = launch_block<8, true, false, false, 4>(g, A, T, 0, st);

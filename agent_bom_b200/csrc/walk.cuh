@@ -63,57 +63,71 @@ struct WalkArgs {
 __device__ __forceinline__ unsigned lanemask_lt(int lane) { return (1u << lane) - 1u; }
 
 // ---------------------------------------------------------------- tier S store
+// Visited set = open addressing in BUCKETS of four 32-bit slots (16 bytes): a probe is ONE ld.shared.v4 plus four compares,
+// and with at most Q entries in H = 4·Q slots a second bucket is almost never needed — the revisit-dominated inner loop of
+// the walk (>90 % of all scanned entries on clique-shaped estates) has no data-dependent loop in the common case.  Slots of
+// a bucket fill in order and nothing is ever deleted during a walk, so an EMPTY last slot ends an unsuccessful probe.
+// The table is wiped with vector stores after each walk (H/128 stores per lane) instead of tracking touched slots.
 template <int H, int Q, bool PAR>
 struct SmemStore {
     static constexpr bool kGlobal = false;
-    static constexpr int kBytes = H * 4 + Q * 4 + Q * 2 + Q + (PAR ? Q * 4 : 0);
-    int32_t *htab; int32_t *queue; int32_t *par; uint16_t *tok; uint8_t *dep;
+    static constexpr int kBytes = H * 4 + Q * 4 + Q + (PAR ? Q * 4 : 0);
+    static constexpr int NB = H / 4;                      // buckets
+    int32_t *htab; int32_t *queue; int32_t *par; uint8_t *dep;
+    uint32_t hbase;     // shared-window address of htab: probes use ld.shared directly (no generic-address arithmetic in the hot loop)
     __device__ SmemStore(unsigned char *base) {
         htab = reinterpret_cast<int32_t *>(base);
         queue = htab + H;
         par = PAR ? queue + Q : nullptr;
-        tok = reinterpret_cast<uint16_t *>(queue + Q + (PAR ? Q : 0));
-        dep = reinterpret_cast<uint8_t *>(tok + Q);
+        dep = reinterpret_cast<uint8_t *>(queue + Q + (PAR ? Q : 0));
+        hbase = static_cast<uint32_t>(__cvta_generic_to_shared(base));
+        asm volatile("mov.u32 %0, %0;" : "+r"(hbase));    // opaque: keep it in a register instead of re-deriving it at every probe
     }
     __device__ void init(int lane) {
-        for (int i = lane; i < H; i += 32) htab[i] = EMPTY;
+        for (int i = lane; i < NB; i += 32) reinterpret_cast<int4 *>(htab)[i] = make_int4(EMPTY, EMPTY, EMPTY, EMPTY);
         __syncwarp();
     }
     __device__ __forceinline__ int qcap() const { return Q; }
     __device__ __forceinline__ int max_level() const { return 255; }
-    static_assert((H & (H - 1)) == 0 && Q * 2 <= H, "hash table must be a power of two and at most half full");
+    static_assert((NB & (NB - 1)) == 0 && Q * 4 <= H, "bucket count must be a power of two and the table at most a quarter full");
     static constexpr int log2c(int v) { return v <= 1 ? 0 : 1 + log2c(v >> 1); }
-    __device__ __forceinline__ static uint32_t hash(int32_t k) { return (static_cast<uint32_t>(k) * 0x9E3779B1u) >> (32 - log2c(H)); }
+    __device__ __forceinline__ static uint32_t bucket(int32_t k) { return (static_cast<uint32_t>(k) * 0x9E3779B1u) >> (32 - log2c(NB)); }
+    // k == EMPTY (-1, the value lanes past the end of a row carry) reads as "present": the first bucket with a free slot matches it
     __device__ __forceinline__ bool contains(int32_t k) const {
-        uint32_t h = hash(k);
+        uint32_t b = bucket(k);
         for (;;) {
-            int32_t v = htab[h];
-            if (v == k) return true;
-            if (v == EMPTY) return false;
-            h = (h + 1) & (H - 1);
+            int x, y, z, w;
+            asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(x), "=r"(y), "=r"(z), "=r"(w) : "r"(hbase + b * 16u) : "memory");
+            if ((x == k) | (y == k) | (z == k) | (w == k)) return true;
+            if (w == EMPTY) return false;                  // bucket not full: k would be in it
+            b = (b + 1) & (NB - 1);
         }
     }
-    // true when newly inserted; slot token returned for O(1) clearing
+    // true when newly inserted (t is unused: the table is wiped as a whole)
     __device__ __forceinline__ bool test_and_set(int32_t k, uint32_t &t) {
-        uint32_t h = hash(k);
+        t = 0;
+        uint32_t b = bucket(k);
         for (;;) {
-            int32_t old = atomicCAS(&htab[h], EMPTY, k);
-            if (old == EMPTY) { t = h; return true; }
-            if (old == k) return false;
-            h = (h + 1) & (H - 1);
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+                const int32_t old = atomicCAS(&htab[b * 4 + s], EMPTY, k);
+                if (old == EMPTY) return true;
+                if (old == k) return false;
+            }
+            b = (b + 1) & (NB - 1);
         }
     }
     __device__ __forceinline__ int32_t q_get(int i) const { return queue[i]; }
-    __device__ __forceinline__ void put(int i, int32_t node, int32_t p, uint32_t t, int d) {
-        queue[i] = node; tok[i] = static_cast<uint16_t>(t); dep[i] = static_cast<uint8_t>(d);
+    __device__ __forceinline__ void put(int i, int32_t node, int32_t p, uint32_t, int d) {
+        queue[i] = node; dep[i] = static_cast<uint8_t>(d);
         if (PAR) par[i] = p;
     }
     __device__ __forceinline__ int32_t par_get(int i) const { return PAR ? par[i] : -1; }
     __device__ __forceinline__ int dep_get(int i) const { return dep[i]; }
-    __device__ __forceinline__ void unset(int32_t, uint32_t t) { htab[t] = EMPTY; }
-    __device__ void clear(int count, int lane) {
+    __device__ __forceinline__ void unset(int32_t, uint32_t) {}      // only called right before clear()
+    __device__ void clear(int, int lane) {
         __syncwarp();
-        for (int i = lane; i < count; i += 32) { uint32_t t = tok[i]; if (t != NO_TOK) htab[t] = EMPTY; }
+        for (int i = lane; i < NB; i += 32) reinterpret_cast<int4 *>(htab)[i] = make_int4(EMPTY, EMPTY, EMPTY, EMPTY);
         __syncwarp();
     }
 };
@@ -127,6 +141,8 @@ struct GlobalStore {
     __device__ __forceinline__ int max_level() const { return 0x7FFFFFF0; }
     // read through L2 (ld.cg): the bits are set by L2 atomics, an L1 line could be stale
     __device__ __forceinline__ bool contains(int32_t k) const { return (__ldcg(bits + (k >> 5)) >> (k & 31)) & 1u; }
+    __device__ __forceinline__ void probe_first(int32_t k, uint32_t &h, bool &found, bool &ended) const { h = 0; found = contains(k); ended = true; }
+    __device__ __forceinline__ bool probe_more(int32_t, uint32_t) const { return false; }
     __device__ __forceinline__ bool test_and_set(int32_t k, uint32_t &t) {
         t = 0;
         uint32_t bit = 1u << (k & 31);
@@ -297,6 +313,60 @@ __device__ __forceinline__ bool expand_row(const WalkArgs &A, Store &st, uint32_
     return true;
 }
 
+
+// Lean form of the row mode for the plain single-direction walk (no relationship / traversable filter, no recorded edges): the
+// blast-radius walk itself.  Per 32-candidate chunk the common (all visited) case is one coalesced load, one hash, one 16-byte
+// shared-memory probe and one vote; lanes past the end of a row carry EMPTY, which the probe reports as present.
+template <class Store, class idx_t>
+__device__ __forceinline__ bool expand_window_lean(const WalkArgs &A, Store &st, const Frontier32 &f, bool single, uint32_t nrows, int32_t base, int depth1,
+                                                   int lane, idx_t &tail) {
+    const bool fwd = A.spec.direction == ABB_DIR_FORWARD;
+    const int32_t *__restrict__ nbr = fwd ? A.g.fnbr : A.g.rnbr;
+    const uint8_t *__restrict__ meta = fwd ? A.g.fmeta : A.g.rmeta;
+    // row start / length of frontier node `lane` of the window (uniform when the window holds a single node)
+    const uint32_t my_s = fwd ? f.sF : f.sR;
+    uint32_t my_d = f.total;
+    if (!single) {
+        const uint32_t nx = __shfl_down_sync(FULL, f.excl, 1);
+        my_d = (lane == 31 ? f.total : nx) - f.excl;
+    }
+    for (uint32_t j = 0; j < nrows; j++) {
+        const uint32_t s = single ? my_s : __shfl_sync(FULL, my_s, j);
+        const uint32_t tot = single ? my_d : __shfl_sync(FULL, my_d, j);
+        if (tot == 0) continue;
+        const int32_t *pl = nbr + s + lane;                 // this lane's column of the row, bumped by 32 per chunk
+        const uint32_t rem0 = tot - min(tot, static_cast<uint32_t>(lane));      // entries at or after this lane's column
+        int32_t v1 = rem0 > 0u ? __ldg(pl) : EMPTY;
+        int32_t v2 = rem0 > 32u ? __ldg(pl + 32) : EMPTY;
+        for (uint32_t c0 = 0; c0 < tot; c0 += 32, pl += 32) {
+            const int32_t v = v1;
+            v1 = v2;
+            v2 = (rem0 > c0 + 64u) ? __ldg(pl + 64) : EMPTY;
+            const bool unv = Store::kGlobal ? (v >= 0 && !st.contains(v)) : !st.contains(v);
+            if (__ballot_sync(FULL, unv) == 0u) continue;
+            // rare path: a new node in this chunk.  One row, unfiltered: the first occurrence of a neighbour in the row carries FIRST_PAIR
+            // (an earlier occurrence in an earlier chunk is visited by now), so no match.any is needed.
+            const uint32_t m = unv ? static_cast<uint32_t>(__ldg(meta + (pl - nbr))) : 0u;
+            const bool leader = unv && (m & ABB_META_FIRST_PAIR);
+            uint32_t tok = NO_TOK;
+            const bool isnew = leader && st.test_and_set(v, tok);
+            const unsigned nm = __ballot_sync(FULL, isnew);
+            const int cnt = __popc(nm);
+            if (cnt) {
+                if (tail + cnt > st.qcap()) {
+                    if (isnew) st.unset(v, tok);
+                    st.clear(tail, lane);
+                    return false;
+                }
+                if (isnew) st.put(tail + __popc(nm & lanemask_lt(lane)), v, base + static_cast<int32_t>(j), tok, depth1);
+                tail += cnt;
+            }
+            __syncwarp();
+        }
+    }
+    return true;
+}
+
 // ---------------------------------------------------------------- one query
 // Returns false when the query outgrew the store (caller re-queues it for the next tier).
 template <class Store, bool NEED_META, bool BUDGET>
@@ -395,6 +465,10 @@ __device__ bool walk_one(const WalkArgs &A, Store &st, int64_t q, int lane, uint
             const uint32_t nrows = static_cast<uint32_t>(exp_end - base);
             if (!BUDGET && !(fl & ABB_WALK_TARGET) && (single || f.total >= 4u * nrows)) {
                 // row mode (long rows): one frontier node after the other, in queue order
+                if (!NEED_META && sp.direction != ABB_DIR_BOTH && !(fl & ABB_WALK_EDGES)) {
+                    if (!expand_window_lean<Store, idx_t>(A, st, f, single, nrows, static_cast<int32_t>(base), depth + 1, lane, tail)) return false;
+                    continue;
+                }
                 if (single) {
                     if (!expand_row<Store, NEED_META, idx_t>(A, st, f.sF, f.dF, f.sR, f.total, static_cast<int32_t>(base), depth + 1, lane, tail, rec_edges)) return false;
                 } else {
@@ -583,8 +657,8 @@ __device__ __forceinline__ int64_t next_chunk(unsigned long long *ctl, int lane)
 }
 
 // ---------------------------------------------------------------- kernels
-template <int H, int Q, bool PAR, bool NEED_META, bool BUDGET, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 5) walk_smem_kernel(const WalkArgs A) {
+template <int H, int Q, bool PAR, bool NEED_META, bool BUDGET, int WARPS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(WARPS * 32, MIN_BLOCKS) walk_smem_kernel(const WalkArgs A) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ uint32_t s_hist[WARPS][ABB_N_ENTITY_TYPES];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

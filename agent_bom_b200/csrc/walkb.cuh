@@ -159,7 +159,8 @@ __device__ bool block_walk_one(const WalkArgs &A, BlockStore<QSM, PAR> &st, int6
     while (lvl_begin < lvl_end && (sp.max_depth < 0 || depth < sp.max_depth)) {
         if (depth + 1 > st.max_level()) { wipe(); return false; }
         // level forecast (also warms the row offsets): a level whose candidates exceed several times the room left will outgrow the tier
-        {
+        // (a small frontier cannot: skip the two barriers)
+        if (lvl_end - lvl_begin >= 64) {
             unsigned long long cand = 0;
             for (int fi = lvl_begin + tid; fi < lvl_end; fi += NT) {
                 const int32_t u = st.q_get(fi);
@@ -396,11 +397,14 @@ __global__ void __launch_bounds__(W * 32, MIN_BLOCKS) walk_block_kernel(const Wa
     }
     for (uint32_t i = tid; i < T.slots; i += W * 32) st.tab[i] = B_EMPTY;
     __syncthreads();
+    unsigned long long nxt = 0;
+    if (tid == 0) nxt = atomicAdd(A.ctl, 1ull);
     for (;;) {
-        if (tid == 0) s_b[3] = atomicAdd(A.ctl, 1ull);
+        if (tid == 0) s_b[3] = nxt;
         __syncthreads();
         const int64_t i = static_cast<int64_t>(s_b[3]);
         if (i >= nq) break;
+        if (tid == 0) nxt = atomicAdd(A.ctl, 1ull);          // the next work item is fetched while this one is walked
         const int64_t q = A.qlist ? A.qlist[i] : i;
         const bool ok = block_walk_one<W, QSM, PAR, NEED_META>(A, st, q, s_cnt, s_red, s_hist, s_b);
         if (!ok && tid == 0) {

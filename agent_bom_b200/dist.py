@@ -63,11 +63,21 @@ def _as_tensor(name: str, arr: np.ndarray) -> torch.Tensor:
     return torch.from_numpy(a)
 
 
-def broadcast_csr(host_csr, info: RankInfo, device: torch.device | str) -> tuple[dict, int, int]:
-    """Rank 0 holds ``host_csr`` (others pass None); returns (device tensors, n_nodes, n_entries) on every rank.
+def warm_up(info: RankInfo, device: torch.device | str) -> None:
+    """Create the communicator before anything is timed (NCCL initialises lazily on the first collective)."""
+    if info.world > 1:
+        t = torch.zeros(1, dtype=torch.int32, device=torch.device(device))
+        dist.all_reduce(t)
+        if torch.device(device).type == "cuda":
+            torch.cuda.synchronize()
 
-    Sizes travel first, then each array is broadcast once from rank 0's device
-    copy — over NVLink 5 / NVSwitch with the ``nccl`` backend.
+
+def broadcast_csr(host_csr, info: RankInfo, device: torch.device | str, return_stats: bool = False):
+    """Rank 0 holds ``host_csr`` (others pass None); returns (device tensors, n_nodes, n_entries[, stats]) on every rank.
+
+    The ten CSR arrays travel as ONE packed byte buffer (256-byte aligned fields): rank 0 uploads into its slices, a
+    single broadcast replicates the buffer — over NVLink 5 / NVSwitch with the ``nccl`` backend — and every rank views
+    the fields in place.  ``stats`` times the upload and the collective separately (the collective with CUDA events).
     """
     device = torch.device(device)
     meta = torch.zeros(2, dtype=torch.int64)
@@ -79,17 +89,43 @@ def broadcast_csr(host_csr, info: RankInfo, device: torch.device | str) -> tuple
         meta = m.cpu()
     n_nodes, n_entries = int(meta[0]), int(meta[1])
     lengths = {"fwd_off": n_nodes + 1, "rev_off": n_nodes + 1, "node_type": n_nodes, "node_rank": n_nodes}
-    tensors = {}
+    layout, total = {}, 0
     for name in CSR_FIELDS:
         length = lengths.get(name, n_entries)
-        if info.rank == 0:
-            t = _as_tensor(name, getattr(host_csr, name)).to(device, non_blocking=False)
-            assert t.numel() == length, (name, t.numel(), length)
+        nbytes = length * torch.empty(0, dtype=_TORCH_DTYPE[name]).element_size()
+        layout[name] = (total, nbytes, length)
+        total += (nbytes + 255) & ~255
+    buf = torch.empty(max(total, 256), dtype=torch.uint8, device=device)
+    tensors = {name: buf[off: off + nbytes].view(_TORCH_DTYPE[name]) for name, (off, nbytes, _length) in layout.items()}
+    import time as _time
+
+    t0 = _time.perf_counter()
+    if info.rank == 0:
+        for name in CSR_FIELDS:
+            src = _as_tensor(name, getattr(host_csr, name))
+            assert src.numel() == layout[name][2], (name, src.numel(), layout[name][2])
+            tensors[name].copy_(src)
+    if device.type == "cuda":
+        torch.cuda.synchronize()
+    upload_s = _time.perf_counter() - t0
+    bcast_ms = 0.0
+    if info.world > 1:
+        if device.type == "cuda":
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            dist.barrier()
+            e0.record()
+            dist.broadcast(buf, src=0)
+            e1.record()
+            torch.cuda.synchronize()
+            bcast_ms = e0.elapsed_time(e1)
         else:
-            t = torch.empty(length, dtype=_TORCH_DTYPE[name], device=device)
-        if info.world > 1:
-            dist.broadcast(t, src=0)
-        tensors[name] = t
+            t1 = _time.perf_counter()
+            dist.broadcast(buf, src=0)
+            bcast_ms = 1000.0 * (_time.perf_counter() - t1)
+    if return_stats:
+        stats = {"bytes": int(total), "rank0_upload_s": round(upload_s, 4), "broadcast_ms": round(bcast_ms, 3),
+                 "broadcast_GBps": round(total / 1e9 / (bcast_ms / 1000.0), 1) if bcast_ms > 0 else None, "collectives": 1 if info.world > 1 else 0}
+        return tensors, n_nodes, n_entries, stats
     return tensors, n_nodes, n_entries
 
 
@@ -126,6 +162,16 @@ def sum_over_ranks(value: float, info: RankInfo, device: torch.device | str) -> 
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return float(t.item())
+
+
+def gather_floats(values, info: RankInfo, device: torch.device | str) -> list[list[float]]:
+    """Every rank's list of floats, by rank (diagnostics: per-rank kernel times)."""
+    if info.world == 1:
+        return [[float(v) for v in values]]
+    t = torch.tensor([float(v) for v in values], dtype=torch.float64, device=device)
+    parts = [torch.zeros_like(t) for _ in range(info.world)]
+    dist.all_gather(parts, t)
+    return [[float(x) for x in p.cpu().tolist()] for p in parts]
 
 
 def barrier(info: RankInfo) -> None:

@@ -22,13 +22,34 @@ from .graph.schema import ENTITY_VALUES, N_ENTITY_TYPES
 _vp = C.c_void_p
 
 
-def _view(ptr, n: int, dtype) -> np.ndarray:
-    """Copy ``n`` items from a C pointer into a fresh numpy array."""
+class _Owner:
+    """Keeps a C result object alive for as long as any numpy view of its pinned host arrays exists."""
+
+    def __init__(self, free, handle):
+        self._free, self._handle = free, handle
+
+    def __del__(self):
+        try:
+            if self._handle:
+                self._free(self._handle)
+                self._handle = None
+        except Exception:
+            pass
+
+
+def _view(ptr, n: int, dtype, owner: _Owner | None = None) -> np.ndarray:
+    """``n`` items at a C pointer as a numpy array: a copy by default; with ``owner`` a zero-copy view of the library's
+    pinned host block whose buffer object holds a reference to the owner (so the block outlives every slice of it)."""
     if not ptr or n <= 0:
         return np.zeros(max(n, 0), dtype=dtype)
     nbytes = n * np.dtype(dtype).itemsize
     buf = (C.c_char * nbytes).from_address(ptr)
-    return np.frombuffer(buf, dtype=dtype).copy()
+    if owner is None:
+        return np.frombuffer(buf, dtype=dtype).copy()
+    buf._owner = owner
+    arr = np.frombuffer(buf, dtype=dtype)
+    arr.flags.writeable = False
+    return arr
 
 
 def _i32(a) -> np.ndarray:
@@ -105,7 +126,9 @@ class DeviceGraph:
         self.n_entries = n_entries
         self.device = device
         self._keepalive = keepalive
-        self._lock = threading.Lock()
+        self._lock = threading.Condition()
+        self._users = 0          # library calls in flight on this handle (ctypes releases the GIL inside them)
+        self._closing = False
 
     # ── construction ────────────────────────────────────────────────────
     @classmethod
@@ -132,10 +155,16 @@ class DeviceGraph:
         return cls(h.value, n_nodes, n_entries, device, keepalive=tensors)
 
     def close(self) -> None:
+        """Free the device graph.  Waits for library calls still running on other threads (a REST worker inside a traversal
+        while another thread re-saves the snapshot): the handle is never freed under a caller."""
         with self._lock:
-            if self._h:
-                _lib.load().abb_graph_free(self._h)
-                self._h = None
+            if not self._h:
+                return
+            self._closing = True
+            while self._users:
+                self._lock.wait()
+            h, self._h = self._h, None
+        _lib.load().abb_graph_free(h)
 
     def __del__(self):
         try:
@@ -145,9 +174,33 @@ class DeviceGraph:
 
     @property
     def handle(self):
+        """The raw handle, for calls made while the caller otherwise guarantees the graph stays open."""
         if not self._h:
             raise RuntimeError("DeviceGraph is closed")
         return self._h
+
+    class _Use:
+        def __init__(self, dg):
+            self.dg = dg
+
+        def __enter__(self):
+            dg = self.dg
+            with dg._lock:
+                if not dg._h or dg._closing:
+                    raise RuntimeError("DeviceGraph is closed")
+                dg._users += 1
+            return dg._h
+
+        def __exit__(self, *exc):
+            dg = self.dg
+            with dg._lock:
+                dg._users -= 1
+                if not dg._users:
+                    dg._lock.notify_all()
+
+    def _use(self):
+        """Context manager around a library call: pins the handle against a concurrent ``close()``."""
+        return DeviceGraph._Use(self)
 
     def set_dedup(self, enabled: bool) -> None:
         """Toggle root-frontier de-duplication of single-source batches (results are identical either way)."""
@@ -192,7 +245,9 @@ class DeviceGraph:
         return _lib.load().abb_spec_distances_along(rel_mask & 0xFFFFFFFF, emit_types & 0xFFFFFFFF)
 
     # ── batched walk ────────────────────────────────────────────────────
-    def walk(self, spec, roots, root_off=None, targets=None) -> WalkResult:
+    def walk(self, spec, roots, root_off=None, targets=None, zero_copy: bool = False) -> WalkResult:
+        """One batched traversal through the host-buffer C call.  ``zero_copy=True`` returns read-only numpy views of the
+        library's pinned result blocks instead of copies (the blocks are recycled when the last view is dropped)."""
         lib = _lib.load()
         roots = _i32(roots)
         if root_off is not None:
@@ -202,37 +257,41 @@ class DeviceGraph:
             nq = int(roots.shape[0])
         tg = _i32(targets) if targets is not None else None
         res = _vp()
-        _lib.check(lib.abb_walk_host(self.handle, C.byref(spec), roots.ctypes.data, root_off.ctypes.data if root_off is not None else None,
-                                     tg.ctypes.data if tg is not None else None, nq, C.byref(res)))
-        try:
-            out = self._collect_walk(res, spec.flags)
-        finally:
-            lib.abb_walk_result_free(res)
+        with self._use() as h:
+            _lib.check(lib.abb_walk_host(h, C.byref(spec), roots.ctypes.data, root_off.ctypes.data if root_off is not None else None,
+                                         tg.ctypes.data if tg is not None else None, nq, C.byref(res)))
+        if zero_copy:
+            out = self._collect_walk(res, spec.flags, _Owner(lib.abb_walk_result_free, res))
+        else:
+            try:
+                out = self._collect_walk(res, spec.flags)
+            finally:
+                lib.abb_walk_result_free(res)
         out.kernel_ms = float(lib.abb_last_walk_ms(self.handle))
         return out
 
     @staticmethod
-    def _collect_walk(res, flags: int) -> WalkResult:
+    def _collect_walk(res, flags: int, owner: _Owner | None = None) -> WalkResult:
         lib = _lib.load()
         nq = int(lib.abb_walk_result_queries(res))
         tn = int(lib.abb_walk_result_total_nodes(res))
         te = int(lib.abb_walk_result_total_edges(res))
         out = WalkResult(
-            start=_view(lib.abb_walk_result_start(res), nq, np.int64), count=_view(lib.abb_walk_result_count(res), nq, np.int32),
-            maxd=_view(lib.abb_walk_result_maxd(res), nq, np.int32), flags=_view(lib.abb_walk_result_flags(res), nq, np.int32),
-            nodes=_view(lib.abb_walk_result_nodes(res), tn, np.int32),
+            start=_view(lib.abb_walk_result_start(res), nq, np.int64, owner), count=_view(lib.abb_walk_result_count(res), nq, np.int32, owner),
+            maxd=_view(lib.abb_walk_result_maxd(res), nq, np.int32, owner), flags=_view(lib.abb_walk_result_flags(res), nq, np.int32, owner),
+            nodes=_view(lib.abb_walk_result_nodes(res), tn, np.int32, owner),
             h2d_bytes=int(lib.abb_walk_result_h2d_bytes(res)), d2h_bytes=int(lib.abb_walk_result_d2h_bytes(res)),
         )
         if flags & _lib.WALK_PARENTS:
-            out.parent = _view(lib.abb_walk_result_parent(res), tn, np.int32)
+            out.parent = _view(lib.abb_walk_result_parent(res), tn, np.int32, owner)
         if flags & _lib.WALK_DEPTHS:
-            out.depth = _view(lib.abb_walk_result_depth(res), tn, np.int32)
+            out.depth = _view(lib.abb_walk_result_depth(res), tn, np.int32, owner)
         if flags & _lib.WALK_HIST:
-            out.hist = _view(lib.abb_walk_result_hist(res), nq * N_ENTITY_TYPES, np.uint32).reshape(nq, N_ENTITY_TYPES)
+            out.hist = _view(lib.abb_walk_result_hist(res), nq * N_ENTITY_TYPES, np.uint32, owner).reshape(nq, N_ENTITY_TYPES)
         if flags & _lib.WALK_EDGES:
-            out.estart = _view(lib.abb_walk_result_estart(res), nq, np.int64)
-            out.ecount = _view(lib.abb_walk_result_ecount(res), nq, np.int64)
-            out.edges = _view(lib.abb_walk_result_edges(res), te, np.uint32)
+            out.estart = _view(lib.abb_walk_result_estart(res), nq, np.int64, owner)
+            out.ecount = _view(lib.abb_walk_result_ecount(res), nq, np.int64, owner)
+            out.edges = _view(lib.abb_walk_result_edges(res), te, np.uint32, owner)
         return out
 
     # convenience wrappers named after the reference functions
@@ -250,28 +309,36 @@ class DeviceGraph:
 
     # ── exposure-path rows ──────────────────────────────────────────────
     @staticmethod
-    def _collect_paths(res, nf: int) -> PathRows:
+    def _collect_paths(res, nf: int, owner: _Owner | None = None, expand: bool = True) -> PathRows:
+        """``expand=False`` leaves the flat row arrays empty (only the factorised form — what crossed PCIe — is wrapped)."""
         lib = _lib.load()
         rows = int(lib.abb_paths_result_rows(res))
+        nl, nt = int(lib.abb_paths_result_links(res)), int(lib.abb_paths_result_template_rows(res))
+        if expand:
+            hops = _view(lib.abb_paths_result_hops(res), rows * 4, np.int32, owner).reshape(rows, 4)
+            rels = np.ascontiguousarray(_view(lib.abb_paths_result_rels(res), rows * 4, np.int8, owner).reshape(rows, 4)[:, :3])
+            ncred, ntool = _view(lib.abb_paths_result_ncred(res), rows, np.int32, owner), _view(lib.abb_paths_result_ntool(res), rows, np.int32, owner)
+        else:
+            hops, rels = np.zeros((0, 4), np.int32), np.zeros((0, 3), np.int8)
+            ncred = ntool = np.zeros(0, np.int32)
         return PathRows(
-            off=_view(lib.abb_paths_result_off(res), nf + 1, np.int64), hops=_view(lib.abb_paths_result_hops(res), rows * 4, np.int32).reshape(rows, 4),
-            rels=np.ascontiguousarray(_view(lib.abb_paths_result_rels(res), rows * 4, np.int8).reshape(rows, 4)[:, :3]), ncred=_view(lib.abb_paths_result_ncred(res), rows, np.int32),
-            ntool=_view(lib.abb_paths_result_ntool(res), rows, np.int32),
+            off=_view(lib.abb_paths_result_off(res), nf + 1, np.int64, owner), hops=hops, rels=rels, ncred=ncred, ntool=ntool,
             h2d_bytes=int(lib.abb_paths_result_h2d_bytes(res)), d2h_bytes=int(lib.abb_paths_result_d2h_bytes(res)),
-            link_off=_view(lib.abb_paths_result_link_off(res), nf + 1, np.int64),
-            link_source=_view(lib.abb_paths_result_link_source(res), int(lib.abb_paths_result_links(res)), np.int32),
-            link_rel=_view(lib.abb_paths_result_link_rel(res), int(lib.abb_paths_result_links(res)), np.int8),
-            link_row_off=_view(lib.abb_paths_result_link_row_off(res), int(lib.abb_paths_result_links(res)) + 1, np.int64),
-            link_template=_view(lib.abb_paths_result_link_template(res), int(lib.abb_paths_result_links(res)), np.int64),
-            template=_view(lib.abb_paths_result_template(res), int(lib.abb_paths_result_template_rows(res)) * 4, np.int32).reshape(-1, 4),
-            template_rel=_view(lib.abb_paths_result_template_rel(res), int(lib.abb_paths_result_template_rows(res)) * 2, np.int8).reshape(-1, 2),
+            link_off=_view(lib.abb_paths_result_link_off(res), nf + 1, np.int64, owner),
+            link_source=_view(lib.abb_paths_result_link_source(res), nl, np.int32, owner),
+            link_rel=_view(lib.abb_paths_result_link_rel(res), nl, np.int8, owner),
+            link_row_off=_view(lib.abb_paths_result_link_row_off(res), nl + 1, np.int64, owner),
+            link_template=_view(lib.abb_paths_result_link_template(res), nl, np.int64, owner),
+            template=_view(lib.abb_paths_result_template(res), nt * 4, np.int32, owner).reshape(-1, 4),
+            template_rel=_view(lib.abb_paths_result_template_rel(res), nt * 2, np.int8, owner).reshape(-1, 2),
         )
 
     def exposure_paths_many(self, findings) -> PathRows:
         lib = _lib.load()
         f = _i32(findings)
         res = _vp()
-        _lib.check(lib.abb_paths_host(self.handle, f.ctypes.data, int(f.shape[0]), C.byref(res)))
+        with self._use() as h:
+            _lib.check(lib.abb_paths_host(h, f.ctypes.data, int(f.shape[0]), C.byref(res)))
         try:
             out = self._collect_paths(res, int(f.shape[0]))
         finally:
@@ -279,12 +346,20 @@ class DeviceGraph:
         out.kernel_ms = float(lib.abb_last_paths_ms(self.handle))
         return out
 
-    def exposure_many(self, findings, max_depth: int = 4, collect: bool = True):
-        """One exposure traversal per finding: impact_of + derived exposure-path rows (BASELINE.json's unit of work)."""
+    def exposure_many(self, findings, max_depth: int = 4, collect: bool = True, zero_copy: bool = False):
+        """One exposure traversal per finding: impact_of + derived exposure-path rows (BASELINE.json's unit of work).
+
+        ``zero_copy=True``: read-only numpy views of the pinned result blocks, exposure-path rows in their factorised form
+        (links + templates; ``PathRows.hops`` etc. stay empty — expand with ``exposure_paths_many`` or from the factors)."""
         lib = _lib.load()
         f = _i32(findings)
         wres, pres = _vp(), _vp()
-        _lib.check(lib.abb_exposure_host(self.handle, f.ctypes.data, int(f.shape[0]), max_depth, C.byref(wres), C.byref(pres)))
+        with self._use() as h:
+            _lib.check(lib.abb_exposure_host(h, f.ctypes.data, int(f.shape[0]), max_depth, C.byref(wres), C.byref(pres)))
+        if zero_copy:
+            w = self._collect_walk(wres, _lib.WALK_HIST, _Owner(lib.abb_walk_result_free, wres))
+            p = self._collect_paths(pres, int(f.shape[0]), _Owner(lib.abb_paths_result_free, pres), expand=False)
+            return w, p
         try:
             if collect:
                 w = self._collect_walk(wres, _lib.WALK_HIST)
@@ -305,8 +380,9 @@ class DeviceGraph:
         cu, tu = _i32(ncu), _i32(ntu)
         assert table.size % 75 == 0 and cu.shape[0] == self.n_nodes and tu.shape[0] == self.n_nodes and b.shape[0] == f.shape[0]
         res = _vp()
-        _lib.check(lib.abb_paths_rank_host(self.handle, f.ctypes.data, int(f.shape[0]), b.ctypes.data, table.ctypes.data, table.size // 75, cu.ctypes.data,
-                                           tu.ctypes.data, int(offset), int(limit), C.byref(res)))
+        with self._use() as h:
+            _lib.check(lib.abb_paths_rank_host(h, f.ctypes.data, int(f.shape[0]), b.ctypes.data, table.ctypes.data, table.size // 75, cu.ctypes.data,
+                                               tu.ctypes.data, int(offset), int(limit), C.byref(res)))
         try:
             k = int(lib.abb_rank_result_count(res))
             rows = PathRows(
@@ -323,7 +399,8 @@ class DeviceGraph:
         lib = _lib.load()
         a = _i32(agents)
         res = _vp()
-        _lib.check(lib.abb_dependency_reach_host(self.handle, a.ctypes.data, int(a.shape[0]), rel_mask & 0xFFFFFFFF, vuln_pkg_mask & 0xFFFFFFFF, C.byref(res)))
+        with self._use() as h:
+            _lib.check(lib.abb_dependency_reach_host(h, a.ctypes.data, int(a.shape[0]), rel_mask & 0xFFFFFFFF, vuln_pkg_mask & 0xFFFFFFFF, C.byref(res)))
         try:
             npk = int(lib.abb_reach_n_packages(res))
             nv = int(lib.abb_reach_n_vulns(res))
@@ -347,7 +424,8 @@ class DeviceGraph:
         """uint64 per node: over all sources, the number of BFS-tree paths the node lies strictly inside (``abb_bottleneck_host``)."""
         src = _i32(sources)
         out = np.zeros(self.n_nodes, dtype=np.uint64)
-        _lib.check(_lib.load().abb_bottleneck_host(self.handle, src.ctypes.data, int(src.shape[0]), out.ctypes.data))
+        with self._use() as h:
+            _lib.check(_lib.load().abb_bottleneck_host(h, src.ctypes.data, int(src.shape[0]), out.ctypes.data))
         return out
 
     # ── timing hooks used by bench.py ───────────────────────────────────

@@ -9,6 +9,7 @@ Mirrors ``/root/reference/src/agent_bom/graph/__init__.py:8-100`` for the names 
 from .builder import build_unified_graph_from_report
 from .container import UnifiedGraph
 from .dependency_reach import PackageReachability, ReachabilityReport, VulnerabilityReachability, compute_dependency_reach
+from .envelope import EdgeIndex, exposure_path_for_attack_path, mcp_exposure_path_payload, serialize_attack_path, serialize_attack_paths
 from .exposure import derived_attack_paths, exposure_path_rows, materialize_attack_paths, node_risk_100, ranked_attack_paths
 from .model import AttackPath, UnifiedEdge, UnifiedNode
 from .snapshot import SnapshotGraph, load_snapshot
@@ -17,5 +18,6 @@ from .schema import FINDING_ENTITY_TYPES, SEVERITY_RANK, EntityType, NodeStatus,
 __all__ = [
     "AttackPath", "EntityType", "FINDING_ENTITY_TYPES", "NodeStatus", "PackageReachability", "ReachabilityReport", "RelationshipType", "SEVERITY_RANK", "SnapshotGraph", "load_snapshot",
     "UnifiedEdge", "UnifiedGraph", "UnifiedNode", "VulnerabilityReachability", "build_unified_graph_from_report", "compute_dependency_reach", "derived_attack_paths", "exposure_path_rows",
-    "materialize_attack_paths", "node_risk_100", "ranked_attack_paths",
+    "materialize_attack_paths", "node_risk_100", "ranked_attack_paths", "EdgeIndex", "exposure_path_for_attack_path", "mcp_exposure_path_payload",
+    "serialize_attack_path", "serialize_attack_paths",
 ]

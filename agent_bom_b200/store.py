@@ -24,7 +24,7 @@ from typing import Any
 
 from .graph.container import UnifiedGraph
 from .graph.dependency_reach import ReachabilityReport, compute_dependency_reach
-from .graph.exposure import derived_attack_paths, exposure_path_rows, materialize_attack_paths, ranked_attack_paths
+from .graph.exposure import exposure_path_rows, materialize_attack_paths, ranked_attack_paths
 
 
 class B200UnsupportedOperationError(NotImplementedError):
@@ -32,50 +32,70 @@ class B200UnsupportedOperationError(NotImplementedError):
     (the Neptune adapter's convention: reference api/neptune_graph.py:26-27, 408-411)."""
 
 
+DEFAULT_TENANT = "default"
+
+
+def normalize_tenant(tenant_id: str | None) -> str:
+    """Blank tenants are the default bucket (reference db/graph_store.py:169-172 ``normalize_graph_tenant_id``)."""
+    return (tenant_id or "").strip() or DEFAULT_TENANT
+
+
 class B200GraphStore:
-    def __init__(self, inner=None, *, device: int = 0):
+    """``max_graphs`` bounds the snapshot cache: every cached snapshot pins a device CSR plus its walk workspace in HBM, so the
+    least recently used one is dropped (and freed once no caller is inside it) when a new snapshot would exceed the bound."""
+
+    def __init__(self, inner=None, *, device: int = 0, max_graphs: int = 4):
         self._inner = inner
         self._device = device
+        self._max_graphs = max(1, int(max_graphs))
         self._lock = threading.RLock()
-        self._graphs: dict[tuple[str, str], UnifiedGraph] = {}
-        self._latest: dict[str, str] = {}
+        self._graphs: "dict[tuple[str, str], UnifiedGraph]" = {}     # insertion order = recency (re-inserted on use)
+        self._latest: dict[str, str] = {}                             # only when there is no inner store to ask
 
-    # ── snapshot cache: the device CSR is a cache of a snapshot, keyed (tenant_id, scan_id) ──
+    # ── snapshot cache: the device CSR is a cache of a snapshot, keyed (tenant, scan_id) ──
+    def _remember(self, key: tuple[str, str], g: UnifiedGraph) -> None:
+        """Insert as most recent; evict beyond the bound.  A replaced / evicted graph is only dereferenced: its device memory is
+        released when the last holder lets go (``DeviceGraph.__del__`` → ``close()``, which itself waits for calls in flight),
+        so a REST worker still inside a traversal of the old snapshot keeps a valid handle."""
+        self._graphs.pop(key, None)
+        self._graphs[key] = g
+        while len(self._graphs) > self._max_graphs:
+            del self._graphs[next(iter(self._graphs))]
+
     def save_graph(self, graph) -> None:
         g = graph if isinstance(graph, UnifiedGraph) else UnifiedGraph.from_graph(graph, device=self._device)
+        tenant = normalize_tenant(g.tenant_id)
         with self._lock:
-            key = (g.tenant_id or "", g.scan_id or "")
-            old = self._graphs.pop(key, None)
-            if old is not None and old is not g:
-                old._invalidate()
-            self._graphs[key] = g
-            self._latest[g.tenant_id or ""] = g.scan_id or ""
+            self._remember((tenant, g.scan_id or ""), g)
+            self._latest[tenant] = g.scan_id or ""
         if self._inner is not None:
             self._inner.save_graph(graph)
 
     def latest_snapshot_id(self, *, tenant_id: str = "") -> str:
+        latest = getattr(self._inner, "latest_snapshot_id", None) if self._inner is not None else None
+        if latest is not None:                # the inner store is the source of truth: another process may have written a newer snapshot
+            return latest(tenant_id=tenant_id)
         with self._lock:
-            if tenant_id in self._latest:
-                return self._latest[tenant_id]
-        return self._inner.latest_snapshot_id(tenant_id=tenant_id) if self._inner is not None else ""
+            return self._latest.get(normalize_tenant(tenant_id), "")
 
     def _graph(self, tenant_id: str, scan_id: str) -> UnifiedGraph | None:
+        tenant = normalize_tenant(tenant_id)
+        sid = scan_id or self.latest_snapshot_id(tenant_id=tenant_id)
         with self._lock:
-            sid = scan_id or self._latest.get(tenant_id or "", "")
-            g = self._graphs.get((tenant_id or "", sid))
+            g = self._graphs.get((tenant, sid))
             if g is not None:
+                self._graphs[(tenant, sid)] = self._graphs.pop((tenant, sid))      # most recently used
                 return g
         if self._inner is None:
             return None
-        g = self._load_topology_first(tenant_id, scan_id)
+        g = self._load_topology_first(tenant_id, sid)
         if g is None:
-            loaded = self._inner.load_graph(tenant_id=tenant_id, scan_id=scan_id)
+            loaded = self._inner.load_graph(tenant_id=tenant_id, scan_id=sid)
             if loaded is None or not getattr(loaded, "nodes", None):
                 return None
             g = UnifiedGraph.from_graph(loaded, device=self._device)
         with self._lock:
-            self._graphs[(tenant_id or "", g.scan_id or scan_id)] = g
-            self._latest.setdefault(tenant_id or "", g.scan_id or scan_id)
+            self._remember((tenant, g.scan_id or sid), g)
         return g
 
     def _load_topology_first(self, tenant_id: str, scan_id: str) -> UnifiedGraph | None:
@@ -124,15 +144,15 @@ class B200GraphStore:
                                    deadline_monotonic=deadline_monotonic, traversable_only=traversable_only, relationship_types=relationship_types,
                                    static_only=static_only, dynamic_only=dynamic_only, include_roots=include_roots)
 
-    def _paths(self, g: UnifiedGraph):
-        """Materialised rows win; otherwise derive from topology on the device (reference api/routes/graph.py:1221-1230)."""
-        return derived_attack_paths(g)
-
     def attack_paths_for_sources(self, *, tenant_id: str = "", scan_id: str = "", source_ids: set[str]):
+        """Materialised attack-path rows of the snapshot whose source is in ``source_ids`` — exactly what the reference stores
+        return (api/graph_store.py:792-834: persisted rows only, ``[]`` for an empty source set); nothing is derived here."""
+        if not source_ids:
+            return []
         g = self._graph(tenant_id, scan_id)
         if g is None:
             return []
-        return [p for p in self._paths(g) if p.source in source_ids]
+        return [p for p in g.attack_paths if p.source in source_ids]
 
     def attack_paths(self, *, tenant_id: str = "", scan_id: str = "", offset: int = 0, limit: int = 100):
         g = self._graph(tenant_id, scan_id)

@@ -741,7 +741,252 @@ def centrality_golden():
     print(f"-> {path} {path.stat().st_size / 1024:.0f} KiB")
 
 
+# ── store contract (SURVEY §8 a10 / b): the reference's own stores answer, method by method ─────────────────────────────
+def store_contract():
+    """Replay the store-level scenarios of the reference's tests (tests/test_graph_api.py:845-1020 — SQLite store BFS, reverse
+    impact, persisted attack paths, edge budget — and the ``_RecordingGraphStore`` cases :1133-1456, the reference's model of a
+    complete alternative backend) through the reference's OWN stores and record every method-level answer:
+
+    * ``engine``: a store that delegates to the in-memory engine exactly like ``PostgresGraphStore`` (api/postgres_graph.py:864-931)
+      and ``_RecordingGraphStore`` (tests/test_graph_api.py:1319-1375) do — the contract ``B200GraphStore`` follows;
+    * ``sqlite``: ``SQLiteGraphStore`` on a file it wrote itself (api/graph_store.py:533-790) — recorded next to it so the known
+      deltas (edge budget counts only the traversed direction, silent 5 000 / 25 000 caps) stay visible.
+    """
+    import tempfile
+
+    from agent_bom.api.graph_store import SQLiteGraphStore
+    from agent_bom.graph import AttackPath
+
+    def scen_bfs():            # :845-858
+        g = UnifiedGraph(scan_id="traversal-scan", tenant_id="default")
+        g.add_node(UnifiedNode(id="agent:a", entity_type=AG, label="agent-a"))
+        g.add_node(UnifiedNode(id="server:s", entity_type=SRV, label="server-s"))
+        g.add_node(UnifiedNode(id="vuln:cve", entity_type=VULN, label="CVE-2026-1"))
+        g.add_edge(UnifiedEdge(source="agent:a", target="server:s", relationship=R.USES, traversable=True))
+        g.add_edge(UnifiedEdge(source="server:s", target="vuln:cve", relationship=R.VULNERABLE_TO, traversable=True))
+        return g
+
+    def scen_impact():         # :909-921
+        g = UnifiedGraph(scan_id="impact-scan", tenant_id="default")
+        g.add_node(UnifiedNode(id="agent:a", entity_type=AG, label="agent-a"))
+        g.add_node(UnifiedNode(id="server:s", entity_type=SRV, label="server-s"))
+        g.add_edge(UnifiedEdge(source="agent:a", target="server:s", relationship=R.USES))
+        return g
+
+    def scen_attack_paths():   # :923-959
+        g = UnifiedGraph(scan_id="attack-path-scan", tenant_id="default")
+        g.add_node(UnifiedNode(id="agent:a", entity_type=AG, label="agent-a"))
+        g.add_node(UnifiedNode(id="server:s", entity_type=SRV, label="server-s"))
+        g.add_node(UnifiedNode(id="vuln:cve", entity_type=VULN, label="CVE-2026-1"))
+        g.add_edge(UnifiedEdge(source="agent:a", target="server:s", relationship=R.USES))
+        g.add_edge(UnifiedEdge(source="server:s", target="vuln:cve", relationship=R.VULNERABLE_TO))
+        g.attack_paths.append(AttackPath(source="agent:a", target="vuln:cve", hops=["agent:a", "server:s", "vuln:cve"], edges=["uses", "vulnerable_to"], composite_risk=9.8))
+        return g
+
+    def scen_attack_fields():  # :961-995
+        g = UnifiedGraph(scan_id="attack-path-fields", tenant_id="default")
+        g.add_node(UnifiedNode(id="agent:a", entity_type=AG, label="agent-a"))
+        g.add_node(UnifiedNode(id="tool:shell", entity_type=TOOL, label="run_shell"))
+        g.add_node(UnifiedNode(id="vuln:cve", entity_type=VULN, label="CVE-2026-1"))
+        g.add_edge(UnifiedEdge(source="agent:a", target="tool:shell", relationship=R.REACHES_TOOL))
+        g.add_edge(UnifiedEdge(source="tool:shell", target="vuln:cve", relationship=R.VULNERABLE_TO))
+        g.attack_paths.append(AttackPath(source="agent:a", target="vuln:cve", hops=["agent:a", "tool:shell", "vuln:cve"], edges=["reaches_tool", "vulnerable_to"],
+                                         composite_risk=9.9, summary="agent-a can reach run_shell before CVE-2026-1", credential_exposure=["AWS_SECRET_ACCESS_KEY"],
+                                         tool_exposure=["run_shell"], vuln_ids=["CVE-2026-1"]))
+        g.attack_paths.append(AttackPath(source="agent:a", target="tool:shell", hops=["agent:a", "tool:shell"], edges=["reaches_tool"], composite_risk=4.0))
+        return g
+
+    def scen_budget():         # :997-1020
+        g = UnifiedGraph(scan_id="budget-scan", tenant_id="default")
+        g.add_node(UnifiedNode(id="server:s", entity_type=SRV, label="server-s"))
+        g.add_node(UnifiedNode(id="tool:t", entity_type=TOOL, label="tool-t"))
+        for index in range(3):
+            g.add_node(UnifiedNode(id=f"agent:in-{index}", entity_type=AG, label=f"in-{index}"))
+            g.add_edge(UnifiedEdge(source=f"agent:in-{index}", target="server:s", relationship=R.USES))
+        g.add_edge(UnifiedEdge(source="server:s", target="tool:t", relationship=R.PROVIDES_TOOL))
+        return g
+
+    def scen_recording():      # :1133-1138 — a single-node store
+        g = UnifiedGraph(scan_id="store-scan", tenant_id="default")
+        g.add_node(UnifiedNode(id="agent:a", entity_type=AG, label="agent-a"))
+        return g
+
+    def stamp(g, scan):
+        g.scan_id, g.tenant_id = scan, "default"
+        return g
+
+    scenarios = [
+        ("bfs", scen_bfs(), ["agent:a", "server:s", "vuln:cve", "missing:x"]),
+        ("impact", scen_impact(), ["server:s", "agent:a", "missing:x"]),
+        ("attack_paths", scen_attack_paths(), ["agent:a", "vuln:cve"]),
+        ("attack_fields", scen_attack_fields(), ["agent:a", "tool:shell"]),
+        ("budget", scen_budget(), ["server:s", "agent:in-1", "tool:t"]),
+        ("recording", scen_recording(), ["agent:a", "missing:x"]),
+        ("kat_probe", stamp(kat_probe(), "kat-probe"), None),
+        ("kat_derived", stamp(kat_derived(), "kat-derived"), None),
+        ("estate_dense", stamp(estate(12, dense=(4, 6, 2)), "estate-dense"), None),
+    ]
+
+    class EngineStore:
+        """PostgresGraphStore / _RecordingGraphStore delegation over one in-memory graph."""
+
+        def __init__(self, graph):
+            self.graph = graph
+
+        def bfs_paths(self, *, tenant_id="", scan_id="", source, max_depth=4, traversable_only=True):
+            if not self.graph.has_node(source):
+                return [], set()
+            return (self.graph.bfs(source, max_depth=max_depth, traversable_only=traversable_only),
+                    self.graph.reachable_from(source, max_depth=max_depth, traversable_only=traversable_only, include_source=False))
+
+        def impact_of(self, *, tenant_id="", scan_id="", node_id, max_depth=4):
+            return self.graph.impact_of(node_id, max_depth=max_depth) if self.graph.has_node(node_id) else None
+
+        def traverse_subgraph(self, *, tenant_id="", scan_id="", roots, **kw):
+            return self.graph.traverse_subgraph(roots, **kw)
+
+        def attack_paths_for_sources(self, *, tenant_id="", scan_id="", source_ids):
+            return [p for p in self.graph.attack_paths if p.source in source_ids]
+
+        def attack_paths(self, *, tenant_id="", scan_id="", offset=0, limit=100):
+            paths = sorted(self.graph.attack_paths, key=lambda p: (-p.composite_risk, p.source, p.target))
+            return self.graph.scan_id, self.graph.created_at, paths[offset: offset + limit], len(paths)
+
+    def ap(p):
+        return {"source": p.source, "target": p.target, "hops": list(p.hops), "edges": [enum_value(e) for e in p.edges], "composite_risk": p.composite_risk,
+                "summary": p.summary, "credential_exposure": list(p.credential_exposure), "tool_exposure": list(p.tool_exposure), "vuln_ids": list(p.vuln_ids)}
+
+    def sub(res):
+        g, depth, trunc = res
+        return {"nodes": sorted(g.nodes), "edges": sorted([e.source, e.target, enum_value(e.relationship)] for e in g.edges),
+                "depth_by_node": dict(sorted(depth.items())), "truncated": bool(trunc)}
+
+    trav_cfgs = [
+        dict(direction="forward", max_depth=1, max_edges=1), dict(direction="forward", max_depth=4), dict(direction="reverse", max_depth=4),
+        dict(direction="both", max_depth=3, max_nodes=4), dict(direction="both", max_depth=4, traversable_only=True),
+        dict(direction="forward", max_depth=3, relationship_types={"uses", "depends_on", "contains", "provides_tool"}),
+        dict(direction="both", max_depth=4, static_only=True), dict(direction="reverse", max_depth=2, include_roots=False),
+        dict(direction="both", max_depth=10, max_nodes=5000, max_edges=25000),
+    ]
+    rng = random.Random(77)
+    doc = {"what": "method-level answers of the reference's stores (engine-delegating store and SQLiteGraphStore) for the scenarios of "
+                   "tests/test_graph_api.py:845-1020,1133-1456 and three larger fixtures", "scenarios": []}
+    for name, g, probes in scenarios:
+        ids = list(g.nodes)
+        if probes is None:
+            probes = rng.sample(ids, min(10, len(ids))) + ["missing:x"]
+        tmp = Path(tempfile.mkdtemp()) / "graph.db"
+        sq = SQLiteGraphStore(tmp)
+        sq.save_graph(g)
+        en = EngineStore(g)
+        scan = g.scan_id
+        calls = []
+        for nid in probes:
+            for depth, trav in ((3, True), (4, False), (1, True)):
+                kw = dict(source=nid, max_depth=depth, traversable_only=trav)
+                row = {"method": "bfs_paths", "kwargs": kw}
+                for label, st in (("engine", en), ("sqlite", sq)):
+                    paths, reach = st.bfs_paths(tenant_id="default", scan_id=scan, **kw)
+                    row[label] = {"paths": paths, "reachable": sorted(reach)}
+                calls.append(row)
+            for depth in (3, 4, 0):
+                kw = dict(node_id=nid, max_depth=depth)
+                row = {"method": "impact_of", "kwargs": kw}
+                for label, st in (("engine", en), ("sqlite", sq)):
+                    row[label] = st.impact_of(tenant_id="default", scan_id=scan, **kw)
+                calls.append(row)
+        for cfg in trav_cfgs:
+            roots = [probes[0], probes[-2] if len(probes) > 1 else probes[0], "missing:x"]
+            kw = dict(cfg)
+            if "relationship_types" in kw:
+                kw["relationship_types"] = sorted(kw["relationship_types"])
+            row = {"method": "traverse_subgraph", "kwargs": dict(kw, roots=roots)}
+            for label, st in (("engine", en), ("sqlite", sq)):
+                call_kw = dict(cfg)
+                row[label] = sub(st.traverse_subgraph(tenant_id="default", scan_id=scan, roots=list(roots), **call_kw))
+            calls.append(row)
+        for srcs in ([probes[0]], list(probes), []):
+            row = {"method": "attack_paths_for_sources", "kwargs": {"source_ids": sorted(srcs)}}
+            for label, st in (("engine", en), ("sqlite", sq)):
+                row[label] = sorted((ap(p) for p in st.attack_paths_for_sources(tenant_id="default", scan_id=scan, source_ids=set(srcs))), key=lambda d: (d["source"], d["target"]))
+            calls.append(row)
+        for off, lim in ((0, 10), (1, 1)):
+            row = {"method": "attack_paths", "kwargs": {"offset": off, "limit": lim}}
+            for label, st in (("engine", en), ("sqlite", sq)):
+                sid, _created, paths, total = st.attack_paths(tenant_id="default", scan_id=scan, offset=off, limit=lim)
+                row[label] = {"scan_id": sid, "paths": [ap(p) for p in paths], "total": total}
+            calls.append(row)
+        # unknown snapshot: the None / empty conventions
+        miss = {"bfs_paths": list(sq.bfs_paths(tenant_id="default", scan_id="no-such-scan", source=probes[0], max_depth=3)),
+                "impact_of": sq.impact_of(tenant_id="default", scan_id="no-such-scan", node_id=probes[0], max_depth=3),
+                "attack_paths_for_sources": sq.attack_paths_for_sources(tenant_id="default", scan_id="no-such-scan", source_ids={probes[0]})}
+        miss["bfs_paths"] = [miss["bfs_paths"][0], sorted(miss["bfs_paths"][1])]
+        doc["scenarios"].append({
+            "name": name, "scan_id": scan,
+            "nodes": [[n.id, enum_value(n.entity_type), n.label, n.severity, n.risk_score] for n in g.nodes.values()],
+            "edges": [[e.source, e.target, enum_value(e.relationship), e.direction, bool(e.traversable)] for e in g.edges],
+            "attack_paths": [ap(p) for p in g.attack_paths], "calls": calls, "missing_snapshot": miss,
+        })
+        print(f"store contract {name}: {len(g.nodes)} nodes, {len(g.edges)} edges, {len(calls)} calls")
+    out = OUT / "store"
+    out.mkdir(parents=True, exist_ok=True)
+    with gzip.open(out / "contract.json.gz", "wb") as fh:
+        fh.write(json.dumps(doc, sort_keys=True).encode())
+
+
+# ── ExposurePath envelopes (SURVEY §8 f2) ───────────────────────────────────────────────────────────────────────────────
+def envelope_golden():
+    """REST ``_serialize_attack_path`` (api/routes/graph.py:597-670) and MCP ``_exposure_path_payload`` (mcp_tools/graph.py:78-100)
+    of the unmodified reference for ranked derived paths and for hand-made materialised paths (missing hops, ghost endpoints,
+    pairs without an edge, bidirectional pairs)."""
+    from agent_bom.api.routes.graph import _serialize_attack_path
+    from agent_bom.graph import AttackPath
+    from agent_bom.mcp_tools.graph import _exposure_path_payload
+
+    def node_rec(n):
+        return {"id": n.id, "entity_type": enum_value(n.entity_type), "label": n.label, "severity": n.severity, "risk_score": n.risk_score, "attributes": dict(n.attributes)}
+
+    def edge_rec(e):
+        return {"source": e.source, "target": e.target, "relationship": enum_value(e.relationship), "direction": e.direction, "traversable": bool(e.traversable)}
+
+    def ap(p):
+        d = p.to_dict()
+        d["edges"] = [enum_value(x) for x in d["edges"]]
+        return d
+
+    cases = []
+    probe = kat_probe()
+    manual = [
+        AttackPath(source="a", target="d", hops=["a", "d"], edges=["shares_cred"], composite_risk=55.0, summary="bidirectional pair", vuln_ids=[" CVE-X ", "CVE-X"]),
+        AttackPath(source="", target="", hops=["s", "b", "c"], edges=[], composite_risk=8.5, summary=""),
+        AttackPath(source="s", target="nowhere", hops=["s", "nowhere", "c"], edges=["uses"], composite_risk=3.0, tool_exposure=["t1"], credential_exposure=["K"]),
+        AttackPath(source="c", target="d", hops=["c", "d"], edges=["depends_on", "extra"], composite_risk=95.0),
+    ]
+    graphs = [("kat_derived", kat_derived(), None), ("kat_probe", probe, manual), ("estate_dense", estate(12, dense=(4, 6, 2)), None), ("mesh", mesh_inventory(), None)]
+    for name, g, paths in graphs:
+        g.scan_id = f"{name}-scan"
+        ranked = paths if paths is not None else _derived_attack_paths(g)
+        sample = ranked[:120] + ranked[-20:] if len(ranked) > 140 else ranked
+        offs = list(range(len(ranked)))[:120] + list(range(len(ranked)))[-20:] if len(ranked) > 140 else list(range(len(ranked)))
+        rest = [_serialize_attack_path(p, g.edges, nodes_by_id=g.nodes, rank=r + 1, scan_id=g.scan_id) for p, r in zip(sample, offs)]
+        rest_plain = [_serialize_attack_path(p, g.edges) for p in sample[:5]]
+        mcp = [_exposure_path_payload(p, nodes_by_id=g.nodes, edges=g.edges, rank=r + 1, scan_id=g.scan_id) for p, r in zip(sample, offs)]
+        cases.append({"name": name, "scan_id": g.scan_id, "nodes": [node_rec(n) for n in g.nodes.values()], "edges": [edge_rec(e) for e in g.edges],
+                      "paths": [ap(p) for p in sample], "ranks": [r + 1 for r in offs], "rest": rest, "rest_without_nodes": rest_plain, "mcp": mcp})
+        print(f"envelope {name}: {len(sample)} of {len(ranked)} paths")
+    out = OUT / "envelope"
+    out.mkdir(parents=True, exist_ok=True)
+    with gzip.open(out / "envelopes.json.gz", "wb") as fh:
+        fh.write(json.dumps({"cases": cases}, sort_keys=True).encode())
+
+
 def main():
+    if "--envelope-only" in sys.argv:
+        envelope_golden()
+        return
+    if "--store-only" in sys.argv:
+        store_contract()
+        return
     if "--lateral-only" in sys.argv:
         lateral_golden()
         return
@@ -759,6 +1004,8 @@ def main():
         builder_identity()
         snapshot_identity()
         return
+    store_contract()
+    envelope_golden()
     estate_identity()
     builder_identity()
     snapshot_identity()

@@ -22,3 +22,27 @@ def test_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "traversals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
+
+
+def test_reference_arm_ignores_torchrun_thread_cap_and_never_loads_the_engine():
+    """Under torchrun the children inherit OMP_NUM_THREADS=1; the reference arm must still use every host core it may run on,
+    and it must not touch libabb200.so (ABB_LIB points at a file that does not exist: loading the engine would raise)."""
+    import os
+
+    env = dict(os.environ, OMP_NUM_THREADS="1", ABB_LIB="does-not-exist.so", RANK="0", WORLD_SIZE="1")
+    proc = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--workload", "S", "--steps", "1", "--warmup", "3", "--cpu-budget", "0.3", "--gpus", "2"],
+                          capture_output=True, text=True, timeout=600, env=env)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    d = json.loads([ln for ln in proc.stdout.splitlines() if ln.strip()][0])
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    assert d["n_gpus"] == 2 and d["impl"] == "reference"
+    ref = d["cpu_baseline"]["reference_python"]
+    assert ref is None or ref["impact_of"][0]["findings_per_s_single_process"] > 0
+
+
+def test_reference_arm_other_ranks_exit_silently():
+    import os
+
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    proc = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--workload", "S", "--gpus", "2"], capture_output=True, text=True, timeout=120, env=env)
+    assert proc.returncode == 0 and proc.stdout.strip() == ""

@@ -48,8 +48,8 @@ def test_impact_every_tier(key, dedup, tier_config):
         dg.set_dedup(dedup)
         rng = np.random.default_rng(21)
         n = og.n_nodes
-        sources = np.concatenate([rng.integers(0, n, size=min(3000, 4 * n)), np.arange(min(n, 64)), [-1, n + 3]]).astype(np.int32)
-        for depth in (4, 2, 7):
+        sources = np.concatenate([rng.integers(0, n, size=min(1000, 4 * n)), np.arange(min(n, 64)), [-1, n + 3]]).astype(np.int32)
+        for depth in (4, 7):
             want = orc.impact_many(og, sources, depth)
             got = dg.impact_many(sources, depth)
             assert_slices_equal(got, want)
@@ -65,7 +65,7 @@ def test_bfs_parents_every_tier(key, tier_config):
     og, dg = configured(key, tier_config)
     try:
         rng = np.random.default_rng(22)
-        sources = rng.integers(0, og.n_nodes, size=600).astype(np.int32)
+        sources = rng.integers(0, og.n_nodes, size=300).astype(np.int32)
         for depth, trav in ((4, True), (6, False)):
             want = orc.bfs_many(og, sources, depth, trav)
             got = dg.bfs_many(sources, depth, trav)
@@ -82,7 +82,7 @@ def test_masked_distances_every_tier(key, dedup, tier_config):
     try:
         dg.set_dedup(dedup)
         rng = np.random.default_rng(23)
-        sources = rng.integers(0, og.n_nodes, size=500).astype(np.int32)
+        sources = rng.integers(0, og.n_nodes, size=250).astype(np.int32)
         for mask, emit in ((REACH4, 0), (0xFFFFFFFF, 0), (REACH4 | (1 << 5) | (1 << 9), 1 << 3)):
             want = orc.distances_many(og, sources, mask)
             spec = dg.spec_distances(mask, emit)
