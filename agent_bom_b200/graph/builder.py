@@ -119,10 +119,17 @@ def _mappable(version: Any) -> bool:
 
 def build_unified_graph_from_report(report_json: dict[str, Any], *, scan_id: str = "", tenant_id: str = "", device: int = 0,
                                     classify_tool: Callable[[str, str], Iterable[str]] | None = None,
-                                    is_credential_key: Callable[[str], bool] | None = None) -> UnifiedGraph:
+                                    is_credential_key: Callable[[str], bool] | None = None, columnar: bool = False) -> UnifiedGraph:
+    """``columnar=True`` builds the graph as COLUMNS (``graph/columnar.py``): no ``UnifiedNode`` / ``UnifiedEdge`` object is made
+    per node or edge, the CSR comes straight from the index arrays, and records are synthesised only for what a caller touches."""
     is_cred = is_credential_key or _default_is_credential_key
-    g = UnifiedGraph(scan_id=scan_id or report_json.get("scan_id", ""), tenant_id=tenant_id, device=device)
-    g.unhandled_sections = [k for k in UNHANDLED_SECTIONS if report_json.get(k)]
+    if columnar:
+        from .columnar import ColumnSink
+
+        sink = ColumnSink(scan_id=scan_id or report_json.get("scan_id", ""), tenant_id=tenant_id, device=device)
+    else:
+        sink = _ObjectSink(UnifiedGraph(scan_id=scan_id or report_json.get("scan_id", ""), tenant_id=tenant_id, device=device))
+    unhandled = [k for k in UNHANDLED_SECTIONS if report_json.get(k)]
     agents_data = report_json.get("agents", [])
     blast_data = report_json.get("blast_radius", report_json.get("blast_radii", []))
     scan_sources = report_json.get("scan_sources", [])
@@ -139,10 +146,9 @@ def build_unified_graph_from_report(report_json: dict[str, Any], *, scan_id: str
     pending: list[tuple[str, str, Any, str]] = []     # (vuln node, server, package version, severity) for capability-impact edges
 
     def node(nid: str, et: EntityType, label: str, **kw) -> None:
-        g.add_node(UnifiedNode(id=nid, entity_type=et, label=label, data_sources=[source_tag], **kw))
+        sink.node(nid, et, label, source_tag, **kw)
 
-    def edge(src: str, dst: str, rel: RelationshipType, **kw) -> None:
-        g.add_edge(UnifiedEdge(source=src, target=dst, relationship=rel, **kw))
+    edge = sink.edge
 
     def exploitable_via(vuln_id: str, server_id: str, version: Any, severity: str) -> None:
         """vuln -> every tool of the server that has capabilities, if the package version is mappable (builder.py:971-1019)."""
@@ -171,8 +177,8 @@ def build_unified_graph_from_report(report_json: dict[str, Any], *, scan_id: str
         agent_key = agent_id.removeprefix("agent:")
         provider_name = str(agent.get("source") or "local").strip() or "local"
         provider_id = f"provider:{provider_name}"
-        if isinstance(meta.get("cloud_origin"), dict) and "cloud_lineage" not in g.unhandled_sections:
-            g.unhandled_sections.append("cloud_lineage")
+        if isinstance(meta.get("cloud_origin"), dict) and "cloud_lineage" not in unhandled:
+            unhandled.append("cloud_lineage")
         node(provider_id, EntityType.PROVIDER, provider_name)
         node(agent_id, EntityType.AGENT, agent_name, attributes={"agent_type": agent.get("type", agent.get("agent_type", ""))})
         edge(provider_id, agent_id, RelationshipType.HOSTS)
@@ -214,7 +220,7 @@ def build_unified_graph_from_report(report_json: dict[str, Any], *, scan_id: str
                 tool_ids.append(tool_id)
                 caps = _tool_capabilities(tool, classify_tool)
                 node(tool_id, EntityType.TOOL, tool_name, attributes={"capabilities": caps, "server": srv_id, "agent": agent_name})
-                tool_has_caps[tool_id] = bool([c for c in g.nodes[tool_id].attributes.get("capabilities", []) if str(c)])
+                tool_has_caps[tool_id] = bool([c for c in caps if str(c)])     # add_node merges attributes: the stored list is this one
                 server_to_tool_ids[srv_id].append(tool_id)
                 edge(srv_id, tool_id, RelationshipType.PROVIDES_TOOL)
 
@@ -246,7 +252,7 @@ def build_unified_graph_from_report(report_json: dict[str, Any], *, scan_id: str
         vuln_id = f"vuln:{vid}"
         node(vuln_id, EntityType.VULNERABILITY, vid, severity=severity, risk_score=br.get("risk_score", 0))
         pkg_id = f"pkg:{package_key(pkg_name, pkg_version, eco, purl)}" if pkg_name else ""
-        if pkg_name and g.has_node(pkg_id):
+        if pkg_name and sink.has_node(pkg_id):
             edge(pkg_id, vuln_id, RelationshipType.VULNERABLE_TO, weight=SEVERITY_RISK_SCORE.get(severity, 1.0))
         # affected servers: package hosts, narrowed by named servers, narrowed by named agents (builder.py:1083-1137)
         candidates: set[str] = set()
@@ -277,8 +283,13 @@ def build_unified_graph_from_report(report_json: dict[str, Any], *, scan_id: str
 
     # ── lateral movement: shared servers / shared credentials, agent ↔ agent (builder.py:475-507) ──
     for rel, groups, weight in ((RelationshipType.SHARES_SERVER, server_to_agents, 3.0), (RelationshipType.SHARES_CRED, cred_to_agents, 4.0)):
+        done: set[tuple[str, ...]] = set()
         for members in groups.values():
             unique = sorted(set(members))
+            key = tuple(unique)
+            if key in done:          # a second group with the very same members only repeats (source, target, relationship) triples: first wins
+                continue
+            done.add(key)
             for i, a1 in enumerate(unique):
                 for a2 in unique[i + 1:]:
                     edge(a1, a2, rel, direction="bidirectional", weight=weight)
@@ -286,10 +297,31 @@ def build_unified_graph_from_report(report_json: dict[str, Any], *, scan_id: str
     # ── model provenance / dataset cards: nodes only (builder.py:509-554) ──
     for m in report_json.get("model_provenance", []):
         name = m.get("model_name", m.get("name", "unknown"))
-        g.add_node(UnifiedNode(id=f"model:{name}", entity_type=EntityType.MODEL, label=name, data_sources=["model-provenance"]))
+        sink.node(f"model:{name}", EntityType.MODEL, name, "model-provenance")
     cards = report_json.get("dataset_cards")
     if isinstance(cards, dict):
         for d in cards.get("datasets", []):
             name = d.get("name") or d.get("source_file") or "unknown-dataset"
-            g.add_node(UnifiedNode(id=f"dataset:{name}", entity_type=EntityType.DATASET, label=name, data_sources=["dataset-cards"]))
+            sink.node(f"dataset:{name}", EntityType.DATASET, name, "dataset-cards")
+    g = sink.finish()
+    g.unhandled_sections = unhandled
     return g
+
+
+class _ObjectSink:
+    """Default sink: one ``UnifiedNode`` / ``UnifiedEdge`` record per node / edge, merged by ``UnifiedGraph.add_node`` / ``add_edge``."""
+
+    def __init__(self, graph: UnifiedGraph):
+        self.g = graph
+
+    def node(self, nid: str, et: EntityType, label: str, source: str, **kw) -> None:
+        self.g.add_node(UnifiedNode(id=nid, entity_type=et, label=label, data_sources=[source], **kw))
+
+    def edge(self, src: str, dst: str, rel: RelationshipType, **kw) -> None:
+        self.g.add_edge(UnifiedEdge(source=src, target=dst, relationship=rel, **kw))
+
+    def has_node(self, nid: str) -> bool:
+        return self.g.has_node(nid)
+
+    def finish(self) -> UnifiedGraph:
+        return self.g
