@@ -113,6 +113,7 @@ extern "C" int abb_csr_build_host(int32_t n_nodes, int64_t n_edges, const int32_
 constexpr int CTL_WORDS = 64;        // 5 tiers x 4 counters, twice (canonical walks at 0, individual walks at CTL_SET)
 constexpr int CTL_SET = 32;
 constexpr int CTL_FATAL = 4 * 4 + 2;  // last tier's fatal flag inside a set
+constexpr int CTL_ROUTE = 24;         // {heavy hand-offs routed to the big block tier, to the warp tier} inside a set
 
 // ------------------------------------------------------------------ device buffers
 struct DevBuf {
@@ -187,10 +188,11 @@ struct abb_graph {
     // tier bookkeeping
     DevBuf ctl, ov1, ov2, ov3, ov4;
     // block tiers (walkb.cuh): mid = 8 warps, queue + table in shared memory; big = 32 warps, 192 KB table, queue in a global scratch slot per block
-    int block_tiers = 3;              // bit 0: mid tier, bit 1: big tier (ABB_BLOCK_TIERS / abb_graph_set_option)
+    int block_tiers = 2;              // bit 0: mid tier (off by default: measured no faster than G1), bit 1: big tier (ABB_BLOCK_TIERS / abb_graph_set_option)
     int mid_slots = 8192, mid_qcap = 4096, big_slots = 49152, big_qcap = 36864;
     int big_grid = 0;
     int mid_warps = 8;                // ABB_MID_WARPS=4: 4-warp mid blocks
+    int64_t big_limit = 0;            // the big tier takes S1's heavy hand-offs when there are at most this many (default 24 per SM)
     DevBuf b_gq, b_gpar, b_gdep;
     // tier G1: many per-warp slots (bitmap over all nodes + a bounded queue); tier GX: a few slots that can hold a whole-graph walk
     DevBuf g_bitmap, g_queue, g_par, g_dep;
@@ -270,6 +272,8 @@ static int graph_finish_init(abb_graph *g) {
     if (const char *e = getenv("ABB_DEDUP")) g->dedup_enabled = atoi(e) != 0;
     if (const char *e = getenv("ABB_BLOCK_TIERS")) g->block_tiers = atoi(e) & 3;
     g->big_grid = g->sm_count;
+    g->big_limit = 24ll * g->sm_count;
+    if (const char *e = getenv("ABB_BIG_LIMIT")) g->big_limit = atoll(e);
     if (const char *e = getenv("ABB_MID_WARPS")) g->mid_warps = atoi(e) == 4 ? 4 : 8;
     if (const char *e = getenv("ABB_S1_MINB")) g->s1_minb = atoi(e) == 4 ? 4 : 5;
     if (const char *e = getenv("ABB_ZEROCOPY")) g->zero_copy = atoi(e) != 0;
@@ -380,7 +384,10 @@ extern "C" int abb_graph_set_option(abb_graph *g, const char *name, int64_t valu
         if (value < 32 || value > 36864) return fail(ABB_ERR_ARG, "big_qcap must be in [32, 36864]");
         g->big_qcap = static_cast<int>(value);
     } else if (k == "zero_copy") g->zero_copy = value != 0;
-    else return fail(ABB_ERR_ARG, "unknown option '%s'", name);
+    else if (k == "big_limit") {
+        if (value < 0) return fail(ABB_ERR_ARG, "big_limit must be >= 0");
+        g->big_limit = value;
+    } else return fail(ABB_ERR_ARG, "unknown option '%s'", name);
     return ABB_OK;
 }
 extern "C" int64_t abb_graph_get_option(const abb_graph *g, const char *name) {
@@ -391,6 +398,7 @@ extern "C" int64_t abb_graph_get_option(const abb_graph *g, const char *name) {
     if (k == "mid_qcap") return g->mid_qcap;
     if (k == "big_qcap") return g->big_qcap;
     if (k == "zero_copy") return g->zero_copy;
+    if (k == "big_limit") return g->big_limit;
     return -1;
 }
 
@@ -540,30 +548,56 @@ static int ceil_log2_i64(int64_t n) { int b = 1; while ((1ll << b) < n) b++; ret
 
 // Up to five tiers on one stream.  `A` carries spec/io and the first tier's work list (qlist/nq/nq_dev); every later
 // tier reads its work list and count from device memory, so nothing here waits for the GPU.
-//   S1  warp  + shared-memory hash/queue           (<= 256 queue entries)
-//   M   block (8 warps)  + shared-memory hash/queue (<= 4096 entries)                     — walkb.cuh, plain walks only
-//   B   block (32 warps) + 192 KB shared-memory hash, queue in global scratch (<= 36864)  — walkb.cuh, plain walks only
-//   G1  warp  + global bitmap, bounded queue slot  (<= 64K queue entries), 40 warps per SM (ABB_G1_WARPS_PER_SM)
-//   GX  warp  + global bitmap, whole-graph slot    (anything)
+//   S1  warp  + shared-memory bucketed hash/queue   (<= 256 queue entries)
+//   B   block (32 warps) + 192 KB shared-memory hash, queue in global scratch (<= 36864)  — walkb.cuh, plain walks: takes S1's HEAVY hand-offs
+//       (its own hand-offs form a second list the next tier reads after S1's)
+//   M   block (4/8 warps) + shared-memory hash/queue (<= 2048/4096 entries)                — walkb.cuh, plain walks: S1's other hand-offs
+//   G1  warp  + global bitmap, bounded queue slot   (<= 64K queue entries), 40 warps per SM (ABB_G1_WARPS_PER_SM)
+//   GX  warp  + global bitmap, whole-graph slot     (anything)
 // "plain" = no node/edge budget, no target stop, no recorded edges; the others go S1 -> G1 -> GX.
-// ctl: tier t uses ctl[4t .. 4t+3] = {work cursor, overflow count, fatal flag, -}; a skipped tier's counters stay zero.
+// S1 writes a TWO-ENDED hand-off list: queries a forecast calls heavy (roots or one level hold more candidates than the queue) from
+// the front, the rest from the back.  Heavy ones go to the big block tier when it is on;
+// otherwise G1 takes the front part first, so the long walks start at once instead of landing behind thousands of short ones.
+// ctl: tier t uses ctl[4t .. 4t+3] = {work cursor, hand-off count (front), fatal flag, hand-off count (back)}; a skipped tier's stay zero.
 static int enqueue_tiers(abb_graph *g, WalkArgs A, int64_t max_items, unsigned long long *ctl, cudaStream_t st) {
     const uint32_t fl = A.spec.flags;
     const bool par = fl & ABB_WALK_PARENTS;
     const bool meta = A.spec.rel_mask != 0xFFFFFFFFu || (fl & ABB_WALK_TRAVERSABLE_ONLY);
     const bool bud = A.spec.max_nodes >= 0 || A.spec.max_edges >= 0;
     int32_t *ovs[4] = {g->ov1.as<int32_t>(), g->ov2.as<int32_t>(), g->ov3.as<int32_t>(), g->ov4.as<int32_t>()};
-    A.ctl = ctl; A.overflow = ovs[0];
+    A.list_cap = max_items;
     A.slice_align = g->slice_align;
+    // S1: two-ended hand-off list in ovs[0]
+    A.ctl = ctl; A.overflow = ovs[0]; A.ov_cnt_front = ctl + 1; A.ov_cnt_back = ctl + 3;
     if (int rc = launch_smem_variant<S1_H, S1_Q, S1_WARPS>(g, A, max_items, par, meta, bud, st)) return rc;
-    int prev = 0;                                   // tier whose overflow list feeds the next launch
-    auto chain = [&](int tier, int32_t *next_ov) {
-        A.qlist = ovs[prev]; A.nq = 0; A.nq_dev = ctl + 4 * prev + 1; A.ctl = ctl + 4 * tier; A.overflow = next_ov;
-    };
     const int idb = ceil_log2_i64(std::max<int64_t>(g->v.n, 2));
     const bool plain = !bud && !(fl & (ABB_WALK_TARGET | ABB_WALK_EDGES));
+    bool front_taken = false;                       // S1's heavy part routed (to the big tier when few, else first in line for the warp tier)
+    unsigned long long *to_big = ctl + CTL_ROUTE, *to_warp = ctl + CTL_ROUTE + 1;
+    if (plain && (g->block_tiers & 2) && idb <= 26) {
+        route_heavy_kernel<<<1, 1, 0, st>>>(ctl + 1, to_big, to_warp, static_cast<unsigned long long>(g->big_limit));
+        g_launches++;
+        // big tier: the heavy (front) part of S1's list; what it cannot hold goes to a list of its own (ovs[2]) that the next tier
+        // reads after S1's back part — NOT onto S1's list: front + back may already fill it
+        A.qlist = ovs[0]; A.nq = 0; A.nq_dev = to_big; A.nq_back_dev = nullptr; A.ctl = ctl + 4 * 1;
+        A.overflow = ovs[2]; A.ov_cnt_front = ctl + 4 * 1 + 1; A.ov_cnt_back = nullptr;
+        const size_t words = static_cast<size_t>(g->big_grid) * g->big_qcap;
+        if (int rc = g->b_gq.ensure(words * 4)) return rc;
+        if (par) if (int rc = g->b_gpar.ensure(words * 4)) return rc;
+        if (fl & ABB_WALK_DEPTHS) if (int rc = g->b_gdep.ensure(words * 4)) return rc;
+        BlockTier T{static_cast<uint32_t>(g->big_slots), g->big_qcap, idb, g->b_gq.as<int32_t>(), g->b_gpar.as<int32_t>(), g->b_gdep.as<int32_t>()};
+        int rc = meta ? launch_block<32, false, true, true, 1>(g, A, T, g->big_grid, st) : launch_block<32, false, true, false, 1>(g, A, T, g->big_grid, st);
+        if (rc) return rc;
+        front_taken = true;
+    }
+    // what the next tier reads: S1's list (its back part, or front then back), or the mid tier's plain list
+    const unsigned long long *in_front = front_taken ? to_warp : ctl + 1, *in_back = ctl + 3;
+    int32_t *in_list = ovs[0];
+    const int32_t *in_list2 = front_taken ? ovs[2] : nullptr;
+    const unsigned long long *in_cnt2 = front_taken ? ctl + 4 * 1 + 1 : nullptr;
     if (plain && (g->block_tiers & 1) && idb <= 28) {
-        chain(1, ovs[1]);
+        A.qlist = in_list; A.nq = 0; A.nq_dev = in_front; A.nq_back_dev = in_back; A.qlist2 = in_list2; A.nq2_dev = in_cnt2; A.ctl = ctl + 4 * 2;
+        A.overflow = ovs[1]; A.ov_cnt_front = ctl + 4 * 2 + 1; A.ov_cnt_back = nullptr;
         BlockTier T{static_cast<uint32_t>(g->mid_slots), g->mid_qcap, idb, nullptr, nullptr, nullptr};
         int rc;
         if (g->mid_warps == 4) {               // 4-warp blocks: half the table / queue, twice the walks in flight per SM
@@ -577,25 +611,16 @@ static int enqueue_tiers(abb_graph *g, WalkArgs A, int64_t max_items, unsigned l
         else if (meta) rc = launch_block<8, true, false, true, 4>(g, A, T, 0, st);
         else rc = launch_block<8, true, false, false, 4>(g, A, T, 0, st);
         if (rc) return rc;
-        prev = 1;
+        in_list = ovs[1]; in_front = ctl + 4 * 2 + 1; in_back = nullptr; in_list2 = nullptr; in_cnt2 = nullptr;
     }
-    if (plain && (g->block_tiers & 2) && idb <= 26) {
-        chain(2, ovs[2]);
-        const size_t words = static_cast<size_t>(g->big_grid) * g->big_qcap;
-        if (int rc = g->b_gq.ensure(words * 4)) return rc;
-        if (par) if (int rc = g->b_gpar.ensure(words * 4)) return rc;
-        if (fl & ABB_WALK_DEPTHS) if (int rc = g->b_gdep.ensure(words * 4)) return rc;
-        BlockTier T{static_cast<uint32_t>(g->big_slots), g->big_qcap, idb, g->b_gq.as<int32_t>(), g->b_gpar.as<int32_t>(), g->b_gdep.as<int32_t>()};
-        int rc = meta ? launch_block<32, false, true, true, 1>(g, A, T, g->big_grid, st) : launch_block<32, false, true, false, 1>(g, A, T, g->big_grid, st);
-        if (rc) return rc;
-        prev = 2;
-    }
-    chain(3, ovs[3]);
+    // G1
+    A.qlist = in_list; A.nq = 0; A.nq_dev = in_front; A.nq_back_dev = in_back; A.qlist2 = in_list2; A.nq2_dev = in_cnt2; A.ctl = ctl + 4 * 3;
+    A.overflow = ovs[3]; A.ov_cnt_front = ctl + 4 * 3 + 1; A.ov_cnt_back = nullptr;
     A.g_bitmap = g->g_bitmap.as<uint32_t>(); A.g_queue = g->g_queue.as<int32_t>(); A.g_par = g->g_par.as<int32_t>(); A.g_dep = g->g_dep.as<int32_t>();
     A.g_words = g->g_words; A.g_qcap = g->g_qcap;
     if (int rc = launch_global_variant(A, g->g_slots, g->sm_count, meta, bud, st)) return rc;
-    prev = 3;
-    chain(4, nullptr);
+    // GX
+    A.qlist = ovs[3]; A.nq_dev = ctl + 4 * 3 + 1; A.nq_back_dev = nullptr; A.qlist2 = nullptr; A.nq2_dev = nullptr; A.ctl = ctl + 4 * 4; A.overflow = nullptr; A.ov_cnt_front = A.ov_cnt_back = nullptr;
     A.g_bitmap = g->x_bitmap.as<uint32_t>(); A.g_queue = g->x_queue.as<int32_t>(); A.g_par = g->x_par.as<int32_t>(); A.g_dep = g->x_dep.as<int32_t>();
     A.g_qcap = g->x_qcap;
     return launch_global_variant(A, g->x_slots, g->sm_count, meta, bud, st);
@@ -645,7 +670,7 @@ static int enqueue_dedup_walk(abb_graph *g, const abb_walk_spec *spec, const abb
     dedup_sig_kernel<<<blocks, 256, 0, st>>>(g->v, *spec, io->roots, nq, sig, qi); g_launches++;
     // temp storage: the largest of the cub calls below
     size_t t_sort = 0, t_scan = 0, t_sel = 0, t_scan2 = 0;
-    CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, t_sort, sig, ssig, qi, sq, static_cast<int>(nq), 0, 64, st));
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, t_sort, sig, ssig, qi, sq, static_cast<int>(nq), 0, SIG_BITS, st));
     cub::TransformInputIterator<int64_t, HeadToI64, const uint8_t *> head64(head, HeadToI64());
     CUDA_TRY(cub::DeviceScan::InclusiveSum(nullptr, t_scan, head64, gid, static_cast<int>(nq), st));
     cub::CountingInputIterator<int64_t> iota(0);
@@ -653,7 +678,7 @@ static int enqueue_dedup_walk(abb_graph *g, const abb_walk_spec *spec, const abb
     CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, t_scan2, glen, goff, static_cast<int>(nq + 1), st));
     size_t tmp = std::max(std::max(t_sort, t_scan), std::max(t_sel, t_scan2)) + 256;
     if ((rc = g->dd_tmp.ensure(tmp))) return rc;
-    CUDA_TRY(cub::DeviceRadixSort::SortPairs(g->dd_tmp.p, t_sort, sig, ssig, qi, sq, static_cast<int>(nq), 0, 64, st)); g_launches++;
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(g->dd_tmp.p, t_sort, sig, ssig, qi, sq, static_cast<int>(nq), 0, SIG_BITS, st)); g_launches++;
     dedup_heads_kernel<<<blocks, 256, 0, st>>>(ssig, sq, nq, head, indiv, cnt); g_launches++;
     CUDA_TRY(cub::DeviceScan::InclusiveSum(g->dd_tmp.p, t_scan, head64, gid, static_cast<int>(nq), st)); g_launches++;
     CUDA_TRY(cub::DeviceSelect::Flagged(g->dd_tmp.p, t_sel, iota, head, hp, cnt, static_cast<int>(nq), st)); g_launches++;
@@ -762,8 +787,13 @@ extern "C" int abb_last_walk_tier_counts(abb_graph *g, int64_t *out8) {
     std::lock_guard<std::mutex> lk(g->mu);
     unsigned long long c[CTL_WORDS];
     CUDA_TRY(cudaMemcpy(c, g->ctl.p, sizeof c, cudaMemcpyDeviceToHost));
-    for (int set = 0; set < 2; set++)
-        for (int t = 0; t < 4; t++) out8[set * 4 + t] = static_cast<int64_t>(c[set * CTL_SET + 4 * t + 1]);
+    for (int set = 0; set < 2; set++) {
+        const unsigned long long *k = c + set * CTL_SET;
+        out8[set * 4 + 0] = static_cast<int64_t>(k[1] + k[3]);          // S1 hand-offs (heavy + other)
+        out8[set * 4 + 1] = static_cast<int64_t>(k[1]);                 // of which heavy (to the big block tier, or first in line for G1)
+        out8[set * 4 + 2] = static_cast<int64_t>(k[4 * 2 + 1]);         // mid block tier hand-offs
+        out8[set * 4 + 3] = static_cast<int64_t>(k[4 * 3 + 1]);         // G1 hand-offs (to GX)
+    }
     return ABB_OK;
 }
 

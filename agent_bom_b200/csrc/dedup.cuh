@@ -23,7 +23,11 @@
 namespace abb {
 
 constexpr int L1_CAP = 8;
-constexpr unsigned long long SIG_INELIGIBLE = 0x8000000000000000ull;
+// Signatures live in the low SIG_BITS bits so the radix sort only passes over those (a 48-bit hash still makes a false match
+// between two of ~10^7 frontiers a 10^-1-per-batch event at worst, and every match is verified element-wise anyway);
+// bit SIG_BITS-1 marks an ineligible source, whose key is its own query index (sorted behind every eligible one).
+constexpr int SIG_BITS = 48;
+constexpr unsigned long long SIG_INELIGIBLE = 1ull << (SIG_BITS - 1);
 
 __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
     x += 0x9E3779B97F4A7C15ull;
@@ -69,7 +73,7 @@ __global__ void dedup_sig_kernel(GraphView g, abb_walk_spec sp, const int32_t *r
     } else {
         h = mix64(0xABB200ull + n);
         for (int i = 0; i < n; i++) h = mix64(h ^ (static_cast<unsigned long long>(static_cast<uint32_t>(lst[i])) + (static_cast<unsigned long long>(i + 1) << 32)));
-        h &= ~SIG_INELIGIBLE;
+        h &= SIG_INELIGIBLE - 1ull;
     }
     sig[q] = h;
     if (qidx) qidx[q] = static_cast<int32_t>(q);

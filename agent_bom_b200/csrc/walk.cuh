@@ -44,9 +44,15 @@ struct WalkArgs {
     abb_walk_io io;
     const int32_t *qlist;        // queries of this launch (NULL = 0..nq-1)
     int64_t nq;
-    const unsigned long long *nq_dev;  // when set, the query count is read from device memory (overflow tiers)
-    unsigned long long *ctl;     // [0] work counter, [1] overflow count, [2] fatal flag
-    int32_t *overflow;           // query ids that outgrew this tier
+    const unsigned long long *nq_dev;  // when set, the query count is read from device memory (overflow tiers): entries qlist[0 .. *nq_dev)
+    const unsigned long long *nq_back_dev;   // second part of a two-ended work list: entries qlist[list_cap-1 .. list_cap-*nq_back_dev], taken after the front part
+    const int32_t *qlist2;       // a second work list, taken after the first (the big block tier's hand-offs, joined to S1's for the next tier)
+    const unsigned long long *nq2_dev;
+    int64_t list_cap;            // capacity of qlist / overflow (a two-ended list grows from both ends)
+    unsigned long long *ctl;     // [0] work counter, [1] overflow count (front), [2] fatal flag, [3] overflow count (back)
+    int32_t *overflow;           // query ids that outgrew this tier: HEAVY ones (forecast says thousands of nodes) from the front, the others
+                                 // from the back when ov_cnt_back is set — the next tier then starts the heavy walks first (or a block tier takes them)
+    unsigned long long *ov_cnt_front, *ov_cnt_back;
     // tier G scratch (per warp slot)
     uint32_t *g_bitmap; int32_t *g_queue; int32_t *g_par; int32_t *g_dep;
     int64_t g_words, g_qcap;
@@ -61,6 +67,34 @@ struct WalkArgs {
 };
 
 __device__ __forceinline__ unsigned lanemask_lt(int lane) { return (1u << lane) - 1u; }
+
+// ---------------------------------------------------------------- tier work lists
+__device__ __forceinline__ int64_t list_count(const WalkArgs &A) {
+    if (!A.nq_dev && !A.nq_back_dev) return A.nq;
+    int64_t n = 0;
+    if (A.nq_dev) n += static_cast<int64_t>(*A.nq_dev);
+    if (A.nq_back_dev) n += static_cast<int64_t>(*A.nq_back_dev);
+    if (A.nq2_dev) n += static_cast<int64_t>(*A.nq2_dev);
+    return n;
+}
+__device__ __forceinline__ int64_t list_item(const WalkArgs &A, int64_t i) {
+    if (!A.qlist) return i;
+    if (!A.nq_back_dev && !A.nq2_dev) return A.qlist[i];
+    const int64_t front = A.nq_dev ? static_cast<int64_t>(*A.nq_dev) : 0;
+    if (i < front) return A.qlist[i];
+    const int64_t back = A.nq_back_dev ? static_cast<int64_t>(*A.nq_back_dev) : 0;
+    if (i < front + back) return A.qlist[A.list_cap - 1 - (i - front)];
+    return A.qlist2[i - front - back];
+}
+__device__ __forceinline__ void list_append(const WalkArgs &A, int64_t q, bool heavy) {
+    if (A.ov_cnt_back && !heavy) {
+        const unsigned long long k = atomicAdd(A.ov_cnt_back, 1ull);
+        A.overflow[A.list_cap - 1 - static_cast<int64_t>(k)] = static_cast<int32_t>(q);
+    } else {
+        const unsigned long long k = atomicAdd(A.ov_cnt_front, 1ull);
+        A.overflow[k] = static_cast<int32_t>(q);
+    }
+}
 
 // ---------------------------------------------------------------- tier S store
 // Visited set = open addressing in BUCKETS of four 32-bit slots (16 bytes): a probe is ONE ld.shared.v4 plus four compares,
@@ -330,47 +364,58 @@ __device__ __forceinline__ bool expand_window_lean(const WalkArgs &A, Store &st,
         const uint32_t nx = __shfl_down_sync(FULL, f.excl, 1);
         my_d = (lane == 31 ? f.total : nx) - f.excl;
     }
+    // insert the new nodes of one 32-candidate chunk in lane order; false = the store overflowed (already cleared)
+    auto insert_chunk = [&](int32_t v, bool unv, const uint8_t *mp, int32_t parent) -> bool {
+        if (__ballot_sync(FULL, unv) == 0u) return true;
+        // One row, unfiltered: the first occurrence of a neighbour in the row carries FIRST_PAIR — a later occurrence (same or later
+        // chunk) never speaks, an earlier one has already been inserted — so no match.any and no re-probe are needed.
+        const uint32_t m = unv ? static_cast<uint32_t>(__ldg(mp)) : 0u;
+        const bool leader = unv && (m & ABB_META_FIRST_PAIR);
+        uint32_t tok = NO_TOK;
+        const bool isnew = leader && st.test_and_set(v, tok);
+        const unsigned nm = __ballot_sync(FULL, isnew);
+        const int cnt = __popc(nm);
+        if (cnt) {
+            if (tail + cnt > st.qcap()) {
+                if (isnew) st.unset(v, tok);
+                st.clear(tail, lane);
+                return false;
+            }
+            if (isnew) st.put(tail + __popc(nm & lanemask_lt(lane)), v, parent, tok, depth1);
+            tail += cnt;
+        }
+        __syncwarp();
+        return true;
+    };
     for (uint32_t j = 0; j < nrows; j++) {
         const uint32_t s = single ? my_s : __shfl_sync(FULL, my_s, j);
         const uint32_t tot = single ? my_d : __shfl_sync(FULL, my_d, j);
         if (tot == 0) continue;
-        const int32_t *pl = nbr + s + lane;                 // this lane's column of the row, bumped by 32 per chunk
+        const int32_t *pl = nbr + s + lane;                 // this lane's column of the row, bumped by 64 per step
         const uint32_t rem0 = tot - min(tot, static_cast<uint32_t>(lane));      // entries at or after this lane's column
+        // two chunks per step (two independent loads and probes per lane, one vote), the next two already in flight
         int32_t v1 = rem0 > 0u ? __ldg(pl) : EMPTY;
         int32_t v2 = rem0 > 32u ? __ldg(pl + 32) : EMPTY;
-        for (uint32_t c0 = 0; c0 < tot; c0 += 32, pl += 32) {
-            const int32_t v = v1;
-            v1 = v2;
-            v2 = (rem0 > c0 + 64u) ? __ldg(pl + 64) : EMPTY;
-            const bool unv = Store::kGlobal ? (v >= 0 && !st.contains(v)) : !st.contains(v);
-            if (__ballot_sync(FULL, unv) == 0u) continue;
-            // rare path: a new node in this chunk.  One row, unfiltered: the first occurrence of a neighbour in the row carries FIRST_PAIR
-            // (an earlier occurrence in an earlier chunk is visited by now), so no match.any is needed.
-            const uint32_t m = unv ? static_cast<uint32_t>(__ldg(meta + (pl - nbr))) : 0u;
-            const bool leader = unv && (m & ABB_META_FIRST_PAIR);
-            uint32_t tok = NO_TOK;
-            const bool isnew = leader && st.test_and_set(v, tok);
-            const unsigned nm = __ballot_sync(FULL, isnew);
-            const int cnt = __popc(nm);
-            if (cnt) {
-                if (tail + cnt > st.qcap()) {
-                    if (isnew) st.unset(v, tok);
-                    st.clear(tail, lane);
-                    return false;
-                }
-                if (isnew) st.put(tail + __popc(nm & lanemask_lt(lane)), v, base + static_cast<int32_t>(j), tok, depth1);
-                tail += cnt;
-            }
-            __syncwarp();
+        for (uint32_t c0 = 0; c0 < tot; c0 += 64, pl += 64) {
+            const int32_t va = v1, vb = v2;
+            v1 = (rem0 > c0 + 64u) ? __ldg(pl + 64) : EMPTY;
+            v2 = (rem0 > c0 + 96u) ? __ldg(pl + 96) : EMPTY;
+            const bool ua = Store::kGlobal ? (va >= 0 && !st.contains(va)) : !st.contains(va);
+            const bool ub = Store::kGlobal ? (vb >= 0 && !st.contains(vb)) : !st.contains(vb);
+            if (__ballot_sync(FULL, ua | ub) == 0u) continue;
+            const uint8_t *mp = meta + (pl - nbr);
+            if (!insert_chunk(va, ua, mp, base + static_cast<int32_t>(j))) return false;
+            if (!insert_chunk(vb, ub, mp + 32, base + static_cast<int32_t>(j))) return false;
         }
     }
     return true;
 }
 
 // ---------------------------------------------------------------- one query
-// Returns false when the query outgrew the store (caller re-queues it for the next tier).
+// Returns 1 when done; 0 when the query outgrew the store (the caller re-queues it for the next tier); -1 when a forecast says
+// it is a HEAVY one (its roots or one level alone hold more candidates than this tier's queue).
 template <class Store, bool NEED_META, bool BUDGET>
-__device__ bool walk_one(const WalkArgs &A, Store &st, int64_t q, int lane, uint32_t *hist_bins) {
+__device__ int walk_one(const WalkArgs &A, Store &st, int64_t q, int lane, uint32_t *hist_bins) {
     const GraphView &g = A.g;
     const abb_walk_spec &sp = A.spec;
     const abb_walk_io &io = A.io;
@@ -414,7 +459,7 @@ __device__ bool walk_one(const WalkArgs &A, Store &st, int64_t q, int lane, uint
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) deg += __shfl_xor_sync(FULL, deg, o);
-        if (deg > static_cast<uint32_t>(st.qcap())) { st.clear(tail, lane); return false; }
+        if (deg > static_cast<uint32_t>(st.qcap())) { st.clear(tail, lane); return -1; }
     }
     int qflags = 0;
     if (n_roots == 0) qflags |= ABB_QFLAG_NO_ROOT;
@@ -444,7 +489,7 @@ __device__ bool walk_one(const WalkArgs &A, Store &st, int64_t q, int lane, uint
             // (shared-memory tier: only a gross excess counts — on clique-shaped graphs most candidates are revisits, and a wrong
             //  guess costs at most one queue-full of discoveries there)
             const unsigned long long factor = Store::kGlobal ? 3ull : 64ull;
-            if (cand > factor * static_cast<unsigned long long>(st.qcap() - tail) + 64ull) { st.clear(tail, lane); return false; }
+            if (cand > factor * static_cast<unsigned long long>(st.qcap() - tail) + 64ull) { st.clear(tail, lane); return -1; }
         }
         for (idx_t base = lvl_begin; base < lvl_end && !stop; base += 32) {
             const bool single = (lvl_end - base) == 1;
@@ -657,6 +702,13 @@ __device__ __forceinline__ int64_t next_chunk(unsigned long long *ctl, int lane)
 }
 
 // ---------------------------------------------------------------- kernels
+// Who takes S1's heavy hand-offs?  The big block tier walks one of them an order of magnitude faster than a single warp, but only one
+// per SM at a time; with thousands of them the warp tier's 40 walks per SM win on throughput.  One thread decides from the count.
+__global__ void route_heavy_kernel(const unsigned long long *heavy, unsigned long long *to_big, unsigned long long *to_warp, unsigned long long limit) {
+    const unsigned long long h = *heavy;
+    if (h <= limit) { *to_big = h; *to_warp = 0ull; } else { *to_big = 0ull; *to_warp = h; }
+}
+
 template <int H, int Q, bool PAR, bool NEED_META, bool BUDGET, int WARPS, int MIN_BLOCKS>
 __global__ void __launch_bounds__(WARPS * 32, MIN_BLOCKS) walk_smem_kernel(const WalkArgs A) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -665,7 +717,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_BLOCKS) walk_smem_kernel(const
     using Store = SmemStore<H, Q, PAR>;
     constexpr int kStride = (Store::kBytes + 15) & ~15;
     Store st(smem + warp * kStride);
-    const int64_t nq = A.nq_dev ? static_cast<int64_t>(*A.nq_dev) : A.nq;
+    const int64_t nq = list_count(A);
     if (nq == 0) return;
     st.init(lane);
     for (;;) {
@@ -673,10 +725,9 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_BLOCKS) walk_smem_kernel(const
         if (c >= nq) break;
         int64_t ce = c + WORK_CHUNK < nq ? c + WORK_CHUNK : nq;
         for (int64_t i = c; i < ce; i++) {
-            int64_t q = A.qlist ? A.qlist[i] : i;
-            if (!walk_one<Store, NEED_META, BUDGET>(A, st, q, lane, s_hist[warp])) {
-                if (lane == 0) { unsigned long long k = atomicAdd(A.ctl + 1, 1ull); A.overflow[k] = static_cast<int32_t>(q); }
-            }
+            const int64_t q = list_item(A, i);
+            const int r = walk_one<Store, NEED_META, BUDGET>(A, st, q, lane, s_hist[warp]);
+            if (r <= 0 && lane == 0) list_append(A, q, r < 0);
         }
     }
 }
@@ -692,16 +743,16 @@ __global__ void __launch_bounds__(128, MIN_BLOCKS) walk_global_kernel(const Walk
     st.par = (A.g_par && (A.spec.flags & ABB_WALK_PARENTS)) ? A.g_par + slot * A.g_qcap : nullptr;
     st.dep = (A.spec.flags & (ABB_WALK_DEPTHS | ABB_WALK_EDGES)) ? A.g_dep + slot * A.g_qcap : nullptr;
     st.cap = static_cast<int>(A.g_qcap);
-    const int64_t nq = A.nq_dev ? static_cast<int64_t>(*A.nq_dev) : A.nq;
+    const int64_t nq = list_count(A);
     for (;;) {
         unsigned long long v = 0;
         if (lane == 0) v = atomicAdd(A.ctl, 1ull);
         int64_t i = static_cast<int64_t>(__shfl_sync(FULL, v, 0));
         if (i >= nq) break;
-        int64_t q = A.qlist ? A.qlist[i] : i;
-        if (!walk_one<GlobalStore, NEED_META, BUDGET>(A, st, q, lane, s_hist[threadIdx.x >> 5])) {
+        const int64_t q = list_item(A, i);          // a two-ended list hands out its heavy (front) part first
+        if (walk_one<GlobalStore, NEED_META, BUDGET>(A, st, q, lane, s_hist[threadIdx.x >> 5]) <= 0) {
             if (lane == 0) {
-                if (A.overflow) { unsigned long long k = atomicAdd(A.ctl + 1, 1ull); A.overflow[k] = static_cast<int32_t>(q); }   // G1 -> GX
+                if (A.overflow) list_append(A, q, true);   // G1 -> GX
                 else atomicExch(A.ctl + 2, 1ull);   // GX: cannot happen unless the whole-graph scratch is undersized
             }
         }

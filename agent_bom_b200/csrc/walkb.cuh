@@ -170,101 +170,126 @@ __device__ bool block_walk_one(const WalkArgs &A, BlockStore<QSM, PAR> &st, int6
             cand = block_sum<W>(cand, s_red, lane, warp);
             if (cand > 8ull * static_cast<unsigned long long>(st.qcap - tail) + 64ull) { wipe(); return false; }
         }
-        for (int win = lvl_begin; win < lvl_end; win += 32) {
-            const int fi = win + lane;
-            const bool fvalid = fi < lvl_end;
-            const int32_t u = fvalid ? st.q_get(fi) : 0;
-            const Frontier32 f = load_frontier(g, sp.direction, u, fvalid);     // identical in every warp
-            for (uint32_t t0 = 0; t0 < f.total; t0 += W * B_CAP) {
-                const uint32_t rem = (f.total - t0 < static_cast<uint32_t>(W * B_CAP)) ? f.total - t0 : static_cast<uint32_t>(W * B_CAP);
-                const uint32_t cap_t = (((rem + W - 1) / W) + 31u) & ~31u;       // this tile's piece per warp (multiple of 32, <= B_CAP)
-                const uint32_t my0 = t0 + warp * cap_t;
-                uint32_t myend = my0 + cap_t; if (myend > t0 + rem) myend = t0 + rem;
-                const int nch = my0 < myend ? static_cast<int>((myend - my0 + 31u) >> 5) : 0;
-
-                // ---- phase 1: fetch (all chunks in flight), probe, claim
-                int32_t cv[B_CH]; uint32_t cmeta[B_CH]; uint32_t cslot[B_CH]; int cown[B_CH]; bool cact[B_CH]; bool ccont[B_CH];
+        // One TILE: every warp holds a contiguous piece [my0, myend) of the flattened candidates of window `f` (whose first frontier node
+        // sits at queue position `wbase`); pieces are ordered by warp.  Returns false (block-uniform) when the queue would overflow.
+        auto tile = [&](const Frontier32 &f, uint32_t my0, uint32_t myend, int wbase) -> bool {
+            const int nch = my0 < myend ? static_cast<int>((myend - my0 + 31u) >> 5) : 0;
+            // ---- phase 1: fetch (all chunks in flight), probe, claim
+            int32_t cv[B_CH]; uint32_t cmeta[B_CH]; uint32_t cslot[B_CH]; int cown[B_CH]; bool cact[B_CH]; bool ccont[B_CH];
 #pragma unroll
-                for (int c = 0; c < B_CH; c++) {
-                    cv[c] = 0; cmeta[c] = 0; cslot[c] = 0; cown[c] = 0; cact[c] = false; ccont[c] = false;
-                    if (c < nch) {
-                        const Cand cd = fetch_cand_lim(g, f, my0 + c * 32 + lane, myend);
-                        cv[c] = cd.nbr; cmeta[c] = cd.meta; cown[c] = cd.owner; cact[c] = cd.active;
-                    }
+            for (int c = 0; c < B_CH; c++) {
+                cv[c] = 0; cmeta[c] = 0; cslot[c] = 0; cown[c] = 0; cact[c] = false; ccont[c] = false;
+                if (c < nch) {
+                    const Cand cd = fetch_cand_lim(g, f, my0 + c * 32 + lane, myend);
+                    cv[c] = cd.nbr; cmeta[c] = cd.meta; cown[c] = cd.owner; cact[c] = cd.active;
                 }
+            }
 #pragma unroll
-                for (int c = 0; c < B_CH; c++) {
-                    if (c < nch) {
-                        const int32_t v = cv[c];
-                        bool pass = cact[c];
-                        if (NEED_META) pass = pass && ((sp.rel_mask >> (cmeta[c] & ABB_META_REL_MASK)) & 1u) && (!(fl & ABB_WALK_TRAVERSABLE_ONLY) || (cmeta[c] & ABB_META_TRAVERSABLE));
-                        // first occurrence of a neighbour inside the chunk speaks for it (see walk.cuh)
-                        bool leader;
-                        const int owner0 = __shfl_sync(FULL, cown[c], 0);
-                        const bool same_owner = __all_sync(FULL, !cact[c] || cown[c] == owner0);
-                        if (!NEED_META && sp.direction != ABB_DIR_BOTH && same_owner) {
-                            leader = pass && (cmeta[c] & ABB_META_FIRST_PAIR);
-                        } else {
-                            const unsigned mm = __match_any_sync(FULL, pass ? v : (-2 - lane));
-                            leader = pass && (__ffs(mm) - 1) == lane;
-                        }
-                        if (leader) {
-                            const uint32_t mine = (myclaim << st.idb) | static_cast<uint32_t>(v);
-                            uint32_t h = st.hash(v);
-                            for (;;) {
-                                uint32_t w = st.tab[h];
-                                if (w == B_EMPTY) {
-                                    w = atomicCAS(&st.tab[h], B_EMPTY, mine);
-                                    if (w == B_EMPTY) { ccont[c] = true; cslot[c] = h; break; }
-                                }
-                                if ((w & st.idmask) == static_cast<uint32_t>(v)) {
-                                    const uint32_t cl = w >> st.idb;
-                                    if (cl != 0u && cl != myclaim) {         // claimed in this tile by another warp: the lower warp wins
-                                        const uint32_t old = atomicMin(&st.tab[h], mine);
-                                        if ((old >> st.idb) > myclaim) { ccont[c] = true; cslot[c] = h; }
-                                    }
-                                    break;                                    // settled (visited) or already claimed by an earlier chunk of this warp
-                                }
-                                h = st.next(h);
+            for (int c = 0; c < B_CH; c++) {
+                if (c < nch) {
+                    const int32_t v = cv[c];
+                    bool pass = cact[c];
+                    if (NEED_META) pass = pass && ((sp.rel_mask >> (cmeta[c] & ABB_META_REL_MASK)) & 1u) && (!(fl & ABB_WALK_TRAVERSABLE_ONLY) || (cmeta[c] & ABB_META_TRAVERSABLE));
+                    // first occurrence of a neighbour inside the chunk speaks for it (see walk.cuh)
+                    bool leader;
+                    const int owner0 = __shfl_sync(FULL, cown[c], 0);
+                    const bool same_owner = __all_sync(FULL, !cact[c] || cown[c] == owner0);
+                    if (!NEED_META && sp.direction != ABB_DIR_BOTH && same_owner) {
+                        leader = pass && (cmeta[c] & ABB_META_FIRST_PAIR);
+                    } else {
+                        const unsigned mm = __match_any_sync(FULL, pass ? v : (-2 - lane));
+                        leader = pass && (__ffs(mm) - 1) == lane;
+                    }
+                    if (leader) {
+                        const uint32_t mine = (myclaim << st.idb) | static_cast<uint32_t>(v);
+                        uint32_t h = st.hash(v);
+                        for (;;) {
+                            uint32_t w = st.tab[h];
+                            if (w == B_EMPTY) {
+                                w = atomicCAS(&st.tab[h], B_EMPTY, mine);
+                                if (w == B_EMPTY) { ccont[c] = true; cslot[c] = h; break; }
                             }
+                            if ((w & st.idmask) == static_cast<uint32_t>(v)) {
+                                const uint32_t cl = w >> st.idb;
+                                if (cl != 0u && cl != myclaim) {         // claimed in this tile by another warp: the lower warp wins
+                                    const uint32_t old = atomicMin(&st.tab[h], mine);
+                                    if ((old >> st.idb) > myclaim) { ccont[c] = true; cslot[c] = h; }
+                                }
+                                break;                                    // settled (visited) or already claimed by an earlier chunk of this warp
+                            }
+                            h = st.next(h);
                         }
                     }
                 }
-                __syncthreads();
-                // ---- phase 2: winners settle their slot; per-warp winner count
-                unsigned wm[B_CH]; int mycnt = 0;
+            }
+            __syncthreads();
+            // ---- phase 2: winners settle their slot; per-warp winner count
+            unsigned wm[B_CH]; int mycnt = 0;
+#pragma unroll
+            for (int c = 0; c < B_CH; c++) {
+                wm[c] = 0u;
+                if (c < nch) {
+                    bool win = false;
+                    if (ccont[c]) {
+                        win = (st.tab[cslot[c]] >> st.idb) == myclaim;
+                        if (win) st.tab[cslot[c]] = static_cast<uint32_t>(cv[c]);
+                    }
+                    wm[c] = __ballot_sync(FULL, win);
+                    mycnt += __popc(wm[c]);
+                }
+            }
+            if (lane == 0) s_cnt[warp] = static_cast<uint32_t>(mycnt);
+            __syncthreads();
+            // ---- phase 3: ordered append
+            uint32_t x = lane < W ? s_cnt[lane] : 0u, incl = x;
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) { const uint32_t y = __shfl_up_sync(FULL, incl, s); if (lane >= s) incl += y; }
+            const int total = static_cast<int>(__shfl_sync(FULL, incl, 31));
+            const int mybase = static_cast<int>(__shfl_sync(FULL, incl - x, warp));
+            if (total) {
+                if (tail + total > st.qcap) return false;
+                int run = tail + mybase;
 #pragma unroll
                 for (int c = 0; c < B_CH; c++) {
-                    wm[c] = 0u;
                     if (c < nch) {
-                        bool win = false;
-                        if (ccont[c]) {
-                            win = (st.tab[cslot[c]] >> st.idb) == myclaim;
-                            if (win) st.tab[cslot[c]] = static_cast<uint32_t>(cv[c]);
-                        }
-                        wm[c] = __ballot_sync(FULL, win);
-                        mycnt += __popc(wm[c]);
+                        if ((wm[c] >> lane) & 1u) st.put(run + __popc(wm[c] & lanemask_lt(lane)), cv[c], wbase + cown[c], depth + 1);
+                        run += __popc(wm[c]);
                     }
                 }
-                if (lane == 0) s_cnt[warp] = static_cast<uint32_t>(mycnt);
-                __syncthreads();
-                // ---- phase 3: ordered append
-                uint32_t x = lane < W ? s_cnt[lane] : 0u, incl = x;
+                tail += total;
+            }
+            return true;
+        };
+        for (int grp = lvl_begin; grp < lvl_end; grp += W * 32) {
+            // MULTI-WINDOW tile: warp w flattens ITS OWN 32 frontier nodes; valid when every one of the W windows fits one piece
+            // (<= B_CAP candidates) — a frontier of short rows is then consumed W*32 nodes per tile instead of 32.
+            const int mywin = grp + warp * 32;
+            const int fi_own = mywin + lane;
+            const bool own_valid = fi_own < lvl_end;
+            const int32_t u_own = own_valid ? st.q_get(fi_own) : 0;
+            const Frontier32 f_own = load_frontier(g, sp.direction, u_own, own_valid);
+            __syncthreads();                                   // s_red may still be read (forecast / previous group)
+            if (lane == 0) s_red[warp] = f_own.total;
+            __syncthreads();
+            unsigned long long mx = lane < W ? s_red[lane] : 0ull;
 #pragma unroll
-                for (int s = 1; s < 32; s <<= 1) { const uint32_t y = __shfl_up_sync(FULL, incl, s); if (lane >= s) incl += y; }
-                const int total = static_cast<int>(__shfl_sync(FULL, incl, 31));
-                const int mybase = static_cast<int>(__shfl_sync(FULL, incl - x, warp));
-                if (total) {
-                    if (tail + total > st.qcap) { wipe(); return false; }
-                    int run = tail + mybase;
-#pragma unroll
-                    for (int c = 0; c < B_CH; c++) {
-                        if (c < nch) {
-                            if ((wm[c] >> lane) & 1u) st.put(run + __popc(wm[c] & lanemask_lt(lane)), cv[c], win + cown[c], depth + 1);
-                            run += __popc(wm[c]);
-                        }
-                    }
-                    tail += total;
+            for (int o = 16; o > 0; o >>= 1) { const unsigned long long y = __shfl_xor_sync(FULL, mx, o); mx = y > mx ? y : mx; }
+            if (mx <= static_cast<unsigned long long>(B_CAP)) {
+                if (!tile(f_own, 0u, f_own.total, mywin)) { wipe(); return false; }
+                continue;
+            }
+            // SHARED-WINDOW tiles: the W windows of the group one after the other, each cut into W pieces
+            for (int win = grp; win < lvl_end && win < grp + W * 32; win += 32) {
+                const int fi = win + lane;
+                const bool fvalid = fi < lvl_end;
+                const int32_t u = fvalid ? st.q_get(fi) : 0;
+                const Frontier32 f = load_frontier(g, sp.direction, u, fvalid);     // identical in every warp
+                for (uint32_t t0 = 0; t0 < f.total; t0 += W * B_CAP) {
+                    const uint32_t rem = (f.total - t0 < static_cast<uint32_t>(W * B_CAP)) ? f.total - t0 : static_cast<uint32_t>(W * B_CAP);
+                    const uint32_t cap_t = (((rem + W - 1) / W) + 31u) & ~31u;       // this tile's piece per warp (multiple of 32, <= B_CAP)
+                    const uint32_t my0 = t0 + warp * cap_t;
+                    uint32_t myend = my0 + cap_t; if (myend > t0 + rem) myend = t0 + rem;
+                    if (!tile(f, my0, myend, win)) { wipe(); return false; }
                 }
             }
         }
@@ -378,7 +403,7 @@ __global__ void __launch_bounds__(W * 32, MIN_BLOCKS) walk_block_kernel(const Wa
     __shared__ uint32_t s_hist[W][ABB_N_ENTITY_TYPES];
     __shared__ unsigned long long s_b[4];
     const int tid = threadIdx.x;
-    const int64_t nq = A.nq_dev ? static_cast<int64_t>(*A.nq_dev) : A.nq;
+    const int64_t nq = list_count(A);
     if (nq == 0) return;
     BlockStore<QSM, PAR> st;
     st.tab = reinterpret_cast<uint32_t *>(smem);
@@ -405,10 +430,10 @@ __global__ void __launch_bounds__(W * 32, MIN_BLOCKS) walk_block_kernel(const Wa
         const int64_t i = static_cast<int64_t>(s_b[3]);
         if (i >= nq) break;
         if (tid == 0) nxt = atomicAdd(A.ctl, 1ull);          // the next work item is fetched while this one is walked
-        const int64_t q = A.qlist ? A.qlist[i] : i;
+        const int64_t q = list_item(A, i);
         const bool ok = block_walk_one<W, QSM, PAR, NEED_META>(A, st, q, s_cnt, s_red, s_hist, s_b);
         if (!ok && tid == 0) {
-            if (A.overflow) { const unsigned long long k = atomicAdd(A.ctl + 1, 1ull); A.overflow[k] = static_cast<int32_t>(q); }
+            if (A.overflow) list_append(A, q, A.ov_cnt_back == nullptr);     // onto the back of a two-ended list when given one
             else atomicExch(A.ctl + 2, 1ull);
         }
     }

@@ -442,7 +442,7 @@ class DeviceGraph:
         """Queries each storage tier of the most recent walk handed to the next tier (first pass / individual pass)."""
         out = (C.c_int64 * 8)()
         _lib.check(_lib.load().abb_last_walk_tier_counts(self.handle, out))
-        names = ("s1", "mid", "big", "g1")
+        names = ("s1", "s1_heavy", "mid", "g1")
         return {"first": dict(zip(names, [int(x) for x in out[0:4]])), "individual": dict(zip(names, [int(x) for x in out[4:8]]))}
 
     def last_paths_ms(self) -> float:

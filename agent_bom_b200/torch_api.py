@@ -27,7 +27,7 @@ def _stream_ptr(stream: torch.cuda.Stream | None):
 
 
 def frontier_signatures(dg: DeviceGraph, spec, roots: torch.Tensor, stream: torch.cuda.Stream | None = None) -> torch.Tensor:
-    """int64 signature of every source's depth-1 frontier (negative = walked individually); equal signatures share a traversal."""
+    """48-bit signature of every source's depth-1 frontier (bit 47 set = walked individually, the key is then the query index); equal signatures share a traversal."""
     assert roots.dtype == torch.int32 and roots.is_cuda
     sig = torch.empty(roots.shape[0], dtype=torch.int64, device=roots.device)
     _lib.check(_lib.load().abb_walk_signatures(dg.handle, C.byref(spec), _ptr(roots), int(roots.shape[0]), _ptr(sig), _stream_ptr(stream)))

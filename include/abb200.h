@@ -109,7 +109,8 @@ int abb_graph_device(const abb_graph *g);
 /* Tuning / test switches of a handle; results never depend on them.  Names: "dedup" (0/1), "block_tiers" (bit 0 = the
  * 8-warp mid tier, bit 1 = the 32-warp big tier of csrc/walkb.cuh; env ABB_BLOCK_TIERS at creation), "mid_qcap" /
  * "big_qcap" (queue entries a block tier accepts before it hands a query to the next tier — the GPU tests shrink them so
- * every hand-off is exercised on small graphs), "zero_copy" (0/1).  get returns -1 for an unknown name. */
+ * every hand-off is exercised on small graphs), "big_limit" (the big tier takes the forecast-heavy queries of a batch when there are
+ * at most this many, otherwise they go first in line to the warp tier; default 24 per SM), "zero_copy" (0/1).  get returns -1 for an unknown name. */
 int abb_graph_set_option(abb_graph *g, const char *name, int64_t value);
 int64_t abb_graph_get_option(const abb_graph *g, const char *name);
 void abb_graph_free(abb_graph *g);
@@ -214,8 +215,9 @@ float abb_last_walk_ms(abb_graph *g);
 /* {queries, frontier groups walked once, sources walked individually, sources eligible for sharing} of the most recent
  * walk on this graph (zeros after the first when the batch was not de-duplicated).  Synchronises the device. */
 int abb_last_walk_stats(abb_graph *g, int64_t *out4);
-/* Queries each storage tier of the most recent walk handed to the next one: out8[0..3] = {S1, mid block, big block, G1}
- * overflow counts of the first pass (canonical walks when de-duplicated), out8[4..7] the same for the individual pass.
+/* Hand-offs between the storage tiers of the most recent walk: out8[0..3] = {queries S1 handed on, of which forecast-heavy
+ * (taken by the big block tier, or first in line for G1), queries the mid block tier handed on, queries G1 handed to GX} for
+ * the first pass (canonical walks when de-duplicated), out8[4..7] the same for the individual pass.
  * Diagnostics for bench.py / the tier tests.  Synchronises the device. */
 int abb_last_walk_tier_counts(abb_graph *g, int64_t *out8);
 float abb_last_paths_ms(abb_graph *g);

@@ -175,3 +175,52 @@ def test_ranked_pages_match_a_host_sort(scale):
         np.testing.assert_array_equal(page.hops, rows.hops[want])
         np.testing.assert_array_equal(page.rels, rows.rels[want])
         np.testing.assert_array_equal(levels[rank], risk[want])
+
+
+def test_L_oracle_replay_including_the_heaviest_sources():
+    """L-scale parity where it is hardest: >= 50 K findings of the 10 M-node / 107 M-edge estate — evenly spaced ones plus the 1 000
+    with the largest forecast reach (the 30 K-node blast radii that cross every tier hand-off) — replayed on the CPU oracle bit for bit:
+    slice order, histograms, max depth, and the exposure-path rows of the same findings."""
+    from agent_bom_b200 import estate
+    from agent_bom_b200.engine import DeviceGraph
+    from agent_bom_b200.graph import csr as csrmod
+    from bench import forecast_weight, host_threads
+
+    est = estate.generate(AGENTS["L"], 2145, estate.BENCH_KNOBS, exact_rank=False)
+    host = csrmod.from_arrays(None, est.node_type, est.src, est.dst, est.rel, est.flags, node_rank=est.node_rank)
+    dg = DeviceGraph.upload(host)
+    og = orc.OracleGraph(n_nodes=host.n_nodes, fwd_off=host.fwd_off, fwd_nbr=host.fwd_nbr, fwd_meta=host.fwd_meta, fwd_eid=host.fwd_eid,
+                         rev_off=host.rev_off, rev_nbr=host.rev_nbr, rev_meta=host.rev_meta, rev_eid=host.rev_eid, node_type=host.node_type)
+    try:
+        f = est.findings
+        w = forecast_weight(host)[f]
+        heavy = f[np.argsort(-w, kind="stable")[:1000]]
+        sel = np.unique(np.concatenate([f[:: max(1, len(f) // 50_000)], heavy])).astype(np.int32)
+        assert len(sel) >= 50_000
+        threads = host_threads()
+        # the device walks ALL findings in one batch (the production shape: frontier groups are shared across the whole batch) ...
+        got_all = dg.impact_many(f, 4)
+        pos = np.searchsorted(f, sel)
+        assert np.array_equal(f[pos], sel)
+        want = orc.impact_many(og, sel, 4, threads=threads)
+        np.testing.assert_array_equal(got_all.count[pos], np.diff(want.off).astype(np.int32))
+        np.testing.assert_array_equal(got_all.hist[pos], want.hist)
+        np.testing.assert_array_equal(got_all.maxd[pos], want.maxd)
+        assert int(np.diff(want.off).max()) > 25_000          # the heavy ones really are in the sample
+        for k, q in enumerate(pos.tolist()):
+            a, b = int(want.off[k]), int(want.off[k + 1])
+            if not np.array_equal(got_all.slice(q), want.nodes[a:b]):
+                raise AssertionError(f"finding {sel[k]}: slice differs from the oracle")
+        # ... and the selected ones alone, as a caller with a small batch would (different grouping, same bits), with their path rows
+        got_w, got_p = dg.exposure_many(sel, 4)
+        np.testing.assert_array_equal(got_w.count, np.diff(want.off).astype(np.int32))
+        for k in range(0, len(sel), 7):
+            a, b = int(want.off[k]), int(want.off[k + 1])
+            np.testing.assert_array_equal(got_w.slice(k), want.nodes[a:b])
+        want_p = orc.derived_paths(og, sel, est.node_rank, threads=threads)
+        np.testing.assert_array_equal(got_p.hops, want_p.hops)
+        np.testing.assert_array_equal(got_p.rels, want_p.rels)
+        np.testing.assert_array_equal(got_p.ncred, want_p.ncred)
+        np.testing.assert_array_equal(got_p.ntool, want_p.ntool)
+    finally:
+        dg.close()

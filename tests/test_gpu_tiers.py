@@ -11,12 +11,15 @@ from test_gpu_parity import REACH4, assert_slices_equal, graphs_for
 
 pytestmark = pytest.mark.gpu
 
+BIG = 1 << 40        # big_limit: the big block tier takes every forecast-heavy query however many there are
 CONFIGS = {
-    "default": dict(block_tiers=3, mid_qcap=4096, big_qcap=36864),
-    "warp-tiers-only": dict(block_tiers=0, mid_qcap=4096, big_qcap=36864),
-    "mid-only": dict(block_tiers=1, mid_qcap=4096, big_qcap=36864),
-    "big-only": dict(block_tiers=2, mid_qcap=4096, big_qcap=36864),
-    "shrunk": dict(block_tiers=3, mid_qcap=300, big_qcap=900),       # most queries of the larger graphs overflow twice
+    "default": dict(block_tiers=2, mid_qcap=4096, big_qcap=36864, big_limit=24 * 148),
+    "warp-tiers-only": dict(block_tiers=0, mid_qcap=4096, big_qcap=36864, big_limit=BIG),
+    "mid-only": dict(block_tiers=1, mid_qcap=4096, big_qcap=36864, big_limit=BIG),
+    "big-always": dict(block_tiers=2, mid_qcap=4096, big_qcap=36864, big_limit=BIG),
+    "big-never-routed": dict(block_tiers=3, mid_qcap=4096, big_qcap=36864, big_limit=0),
+    "all-tiers": dict(block_tiers=3, mid_qcap=4096, big_qcap=36864, big_limit=BIG),
+    "shrunk": dict(block_tiers=3, mid_qcap=300, big_qcap=900, big_limit=BIG),       # most queries of the larger graphs overflow twice
 }
 GRAPHS = [(2000, 12000, 2), (6000, 90000, 3), (30000, 400000, 4), "estate_dense_40"]
 
