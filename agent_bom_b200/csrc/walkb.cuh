@@ -231,8 +231,10 @@ __device__ bool block_walk_one(const WalkArgs &A, BlockStore<QSM, PAR> &st, int6
                 if (c < nch) {
                     bool win = false;
                     if (ccont[c]) {
-                        win = (st.tab[cslot[c]] >> st.idb) == myclaim;
-                        if (win) st.tab[cslot[c]] = static_cast<uint32_t>(cv[c]);
+                        // a losing contender may read the slot while the winner settles it: either value tells it "not mine".  Both
+                        // sides go through atomics so that this intended overlap is not a formal data race (compute-sanitizer racecheck)
+                        win = (atomicAdd(&st.tab[cslot[c]], 0u) >> st.idb) == myclaim;
+                        if (win) atomicExch(&st.tab[cslot[c]], static_cast<uint32_t>(cv[c]));
                     }
                     wm[c] = __ballot_sync(FULL, win);
                     mycnt += __popc(wm[c]);
