@@ -226,7 +226,9 @@ def run_reference(args) -> int:
     t0 = time.perf_counter()
     og = orc.build_csr(est.n_nodes, est.src, est.dst, est.rel, est.flags, est.node_type)
     log(f"[bench] oracle CSR build {time.perf_counter() - t0:.1f}s; {threads} OpenMP threads")
-    sample = sample_for_budget(og, est.findings, est.node_rank, args.cpu_budget, threads, args.mode, min_frac=0.10 if args.workload != "L" else 0.0)
+    # every pass is a bounded sample: the whole --steps K --warmup W run stays within a few minutes (≈150 s of timed CPU work in total)
+    per_pass = max(2.0, min(args.cpu_budget, 150.0 / (args.steps + args.warmup)))
+    sample = sample_for_budget(og, est.findings, est.node_rank, per_pass, threads, args.mode, min_frac=0.10 if args.workload != "L" else 0.0)
     times = []
     for i in range(args.warmup + args.steps):
         dt, _w = cpu_traversals(og, sample, est.node_rank, threads, args.mode)
