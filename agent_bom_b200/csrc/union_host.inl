@@ -1,17 +1,19 @@
 // union_host.inl — host orchestration of abb_group_union_host (included by abb200.cu after reach_host.inl).
 // Reference use: effective_reach.py:372-426 (see union.cuh).
 
-struct abb_union_result {
-    std::vector<int64_t> off;
-    std::vector<int32_t> items;
-    std::vector<uint8_t> w0, w1;
+struct abb_union_result {       // result arrays live in pinned host blocks of the library's pool: D2H at PCIe rate, no zero-fill of fresh vectors
+    HostBlock off, items, w0, w1;
     double ms = 0.0;
 };
-extern "C" void abb_union_result_free(abb_union_result *r) { delete r; }
-extern "C" const int64_t *abb_union_result_off(const abb_union_result *r) { return r->off.data(); }
-extern "C" const int32_t *abb_union_result_items(const abb_union_result *r) { return r->items.data(); }
-extern "C" const uint8_t *abb_union_result_w0(const abb_union_result *r) { return r->w0.data(); }
-extern "C" const uint8_t *abb_union_result_w1(const abb_union_result *r) { return r->w1.data(); }
+extern "C" void abb_union_result_free(abb_union_result *r) {
+    if (!r) return;
+    for (HostBlock *b : {&r->off, &r->items, &r->w0, &r->w1}) b->release();
+    delete r;
+}
+extern "C" const int64_t *abb_union_result_off(const abb_union_result *r) { return r->off.as<int64_t>(); }
+extern "C" const int32_t *abb_union_result_items(const abb_union_result *r) { return r->items.as<int32_t>(); }
+extern "C" const uint8_t *abb_union_result_w0(const abb_union_result *r) { return r->w0.as<uint8_t>(); }
+extern "C" const uint8_t *abb_union_result_w1(const abb_union_result *r) { return r->w1.as<uint8_t>(); }
 extern "C" double abb_union_result_ms(const abb_union_result *r) { return r->ms; }
 
 struct StreamGuard {
@@ -84,13 +86,14 @@ extern "C" int abb_group_union_host(int device, int64_t n_groups, const int64_t 
 
     abb_union_result *r = new abb_union_result();
     float ms = 0.f; cudaEventElapsedTime(&ms, sg.e0, sg.e1); r->ms = ms;
-    r->off.resize(static_cast<size_t>(n_groups) + 1); r->items.resize(static_cast<size_t>(AU));
-    r->w0.resize(static_cast<size_t>(n_groups)); r->w1.resize(static_cast<size_t>(n_groups));
-    cudaError_t e = cudaMemcpy(r->off.data(), poff.p, static_cast<size_t>(n_groups + 1) * 8, cudaMemcpyDeviceToHost);
-    if (e == cudaSuccess && AU) e = cudaMemcpy(r->items.data(), v1.p, static_cast<size_t>(AU) * 4, cudaMemcpyDeviceToHost);
-    if (e == cudaSuccess && n_groups) e = cudaMemcpy(r->w0.data(), gw0.p, static_cast<size_t>(n_groups), cudaMemcpyDeviceToHost);
-    if (e == cudaSuccess && n_groups) e = cudaMemcpy(r->w1.data(), gw1.p, static_cast<size_t>(n_groups), cudaMemcpyDeviceToHost);
-    if (e != cudaSuccess) { delete r; return fail(ABB_ERR_CUDA, "union D2H: %s", cudaGetErrorString(e)); }
+    if (!(r->off.alloc(static_cast<size_t>(n_groups + 1) * 8) && r->items.alloc(static_cast<size_t>(AU) * 4) && r->w0.alloc(static_cast<size_t>(n_groups)) &&
+          r->w1.alloc(static_cast<size_t>(n_groups)))) { abb_union_result_free(r); return fail(ABB_ERR_NOMEM, "pinned host allocation failed"); }
+    cudaError_t e = cudaMemcpyAsync(r->off.p, poff.p, static_cast<size_t>(n_groups + 1) * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && AU) e = cudaMemcpyAsync(r->items.p, v1.p, static_cast<size_t>(AU) * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && n_groups) e = cudaMemcpyAsync(r->w0.p, gw0.p, static_cast<size_t>(n_groups), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && n_groups) e = cudaMemcpyAsync(r->w1.p, gw1.p, static_cast<size_t>(n_groups), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { abb_union_result_free(r); return fail(ABB_ERR_CUDA, "union D2H: %s", cudaGetErrorString(e)); }
     *out = r;
     return ABB_OK;
 }
