@@ -18,6 +18,7 @@
 #include <vector>
 
 #include <cub/cub.cuh>
+#include <nvtx3/nvToolsExt.h>      // header-only; ranges cost nothing unless a profiler is attached
 
 #include "../../include/abb200.h"
 #include "dedup.cuh"
@@ -55,6 +56,12 @@ extern "C" int abb_device_count(void) {
     return n;
 }
 extern "C" int64_t abb_launch_count(void) { return g_launches.load(); }
+
+// NVTX range around every host entry point and the stages inside a walk (Nsight Systems / ncu --nvtx show the C-ABI calls by name)
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 // ------------------------------------------------------------------ (a1) host CSR build
 extern "C" int64_t abb_csr_entries(int64_t n_edges, const uint8_t *flags) {
@@ -182,6 +189,7 @@ struct abb_graph {
     std::mutex mu;                    // serialises use of the shared workspace
     cudaStream_t stream = nullptr;    // host-API stream
     cudaStream_t copy_stream = nullptr;   // result copies that may overlap later kernels of the same call
+    cudaStream_t paths_stream = nullptr;  // exposure-path pipeline of abb_exposure_host, run next to the walk
     cudaEvent_t ev_copy = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool walk_timed = false, paths_timed = false;
@@ -201,7 +209,8 @@ struct abb_graph {
     int x_slots = 0; int64_t x_qcap = 0;
     // root-frontier de-duplication workspace
     DevBuf dd_sig, dd_ssig, dd_q, dd_sq, dd_head, dd_gid, dd_hp, dd_glen, dd_goff, dd_arena, dd_memoff, dd_memsrc, dd_memstate, dd_indiv, dd_cnt, dd_tmp;
-    DevBuf dd_gstart, dd_gcount, dd_gmaxd, dd_gflags, dd_ghist;
+    DevBuf dd_gstart, dd_gcount, dd_gmaxd, dd_gflags, dd_ghist, dd_lkey, dd_lkey2, dd_lgid, dd_order;
+    bool locality_order = true;   // walk the frontier groups in first-seed order (ABB_LOCALITY=0 disables)
     bool dedup_enabled = true;
     int slice_align = 0;        // set while a host-mapped arena is the walk target
     bool align_direct = true;
@@ -241,6 +250,7 @@ static int graph_finish_init(abb_graph *g) {
     g->sm_count = prop.multiProcessorCount;
     CUDA_TRY(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&g->copy_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&g->paths_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&g->ev_copy, cudaEventDisableTiming));
     for (auto &e : g->ev) CUDA_TRY(cudaEventCreate(&e));
     if (int rc = g->ctl.ensure(CTL_WORDS * sizeof(unsigned long long))) return rc;
@@ -271,6 +281,7 @@ static int graph_finish_init(abb_graph *g) {
     }
     if (const char *e = getenv("ABB_DEDUP")) g->dedup_enabled = atoi(e) != 0;
     if (const char *e = getenv("ABB_BLOCK_TIERS")) g->block_tiers = atoi(e) & 3;
+    if (const char *e = getenv("ABB_LOCALITY")) g->locality_order = atoi(e) != 0;
     g->big_grid = g->sm_count;
     g->big_limit = 24ll * g->sm_count;
     if (const char *e = getenv("ABB_BIG_LIMIT")) g->big_limit = atoll(e);
@@ -408,9 +419,10 @@ extern "C" void abb_graph_free(abb_graph *g) {
     { std::lock_guard<std::mutex> lk(g->mu); }      // a host-API call still inside the library finishes before the teardown starts
     if (g->stream) { cudaStreamSynchronize(g->stream); cudaStreamDestroy(g->stream); }
     if (g->copy_stream) { cudaStreamSynchronize(g->copy_stream); cudaStreamDestroy(g->copy_stream); }
+    if (g->paths_stream) { cudaStreamSynchronize(g->paths_stream); cudaStreamDestroy(g->paths_stream); }
     if (g->ev_copy) cudaEventDestroy(g->ev_copy);
     for (auto &e : g->ev) if (e) cudaEventDestroy(e);
-    for (DevBuf *b : {&g->ctl, &g->ov1, &g->ov2, &g->ov3, &g->ov4, &g->b_gq, &g->b_gpar, &g->b_gdep, &g->g_bitmap, &g->g_queue, &g->g_par, &g->g_dep, &g->x_bitmap, &g->x_queue, &g->x_par, &g->x_dep, &g->dd_sig, &g->dd_ssig, &g->dd_q, &g->dd_sq, &g->dd_head, &g->dd_gid, &g->dd_hp, &g->dd_glen, &g->dd_goff, &g->dd_arena, &g->dd_memoff, &g->dd_memsrc, &g->dd_memstate, &g->dd_indiv, &g->dd_cnt, &g->dd_tmp, &g->dd_gstart, &g->dd_gcount, &g->dd_gmaxd, &g->dd_gflags, &g->dd_ghist, &g->identity_rank, &g->d_roots, &g->d_root_off,
+    for (DevBuf *b : {&g->ctl, &g->ov1, &g->ov2, &g->ov3, &g->ov4, &g->b_gq, &g->b_gpar, &g->b_gdep, &g->g_bitmap, &g->g_queue, &g->g_par, &g->g_dep, &g->x_bitmap, &g->x_queue, &g->x_par, &g->x_dep, &g->dd_sig, &g->dd_ssig, &g->dd_q, &g->dd_sq, &g->dd_head, &g->dd_gid, &g->dd_hp, &g->dd_glen, &g->dd_goff, &g->dd_arena, &g->dd_memoff, &g->dd_memsrc, &g->dd_memstate, &g->dd_indiv, &g->dd_cnt, &g->dd_tmp, &g->dd_lkey, &g->dd_lkey2, &g->dd_lgid, &g->dd_order, &g->dd_gstart, &g->dd_gcount, &g->dd_gmaxd, &g->dd_gflags, &g->dd_ghist, &g->identity_rank, &g->d_roots, &g->d_root_off,
                       &g->d_targets, &g->d_qstart, &g->d_qcount, &g->d_qmaxd, &g->d_qflags, &g->d_qestart, &g->d_qecount, &g->d_qhist, &g->d_nodes,
                       &g->d_parent, &g->d_depth, &g->d_edges, &g->d_totals, &g->p_findings, &g->p_counts, &g->p_off, &g->p_hops, &g->p_rels,
                       &g->p_ncred, &g->p_ntool, &g->p_scan_tmp, &g->srv_cred, &g->srv_tool, &g->pl_cnt, &g->pl_off, &g->pl_vs, &g->pl_rel, &g->pl_rows, &g->pl_roff, &g->pl_toff, &g->pl_need, &g->pl_ulist, &g->pl_nu, &g->pt_cnt, &g->pt_off, &g->pt_off_node, &g->pt_cnt_node, &g->pt_row, &g->pt_rel})
@@ -560,6 +572,7 @@ static int ceil_log2_i64(int64_t n) { int b = 1; while ((1ll << b) < n) b++; ret
 // otherwise G1 takes the front part first, so the long walks start at once instead of landing behind thousands of short ones.
 // ctl: tier t uses ctl[4t .. 4t+3] = {work cursor, hand-off count (front), fatal flag, hand-off count (back)}; a skipped tier's stay zero.
 static int enqueue_tiers(abb_graph *g, WalkArgs A, int64_t max_items, unsigned long long *ctl, cudaStream_t st) {
+    NvtxRange nvtx_("walk: storage tiers");
     const uint32_t fl = A.spec.flags;
     const bool par = fl & ABB_WALK_PARENTS;
     const bool meta = A.spec.rel_mask != 0xFFFFFFFFu || (fl & ABB_WALK_TRAVERSABLE_ONLY);
@@ -646,6 +659,7 @@ struct HeadToI64 { __host__ __device__ int64_t operator()(uint8_t v) const { ret
 
 // Group single-source walks by their level-1 frontier, walk each group once, share the slice (dedup.cuh).
 static int enqueue_dedup_walk(abb_graph *g, const abb_walk_spec *spec, const abb_walk_io *io, cudaStream_t st) {
+    NvtxRange nvtx_("walk: root-frontier de-duplication + canonical / individual tiers");
     const int64_t nq = io->n_queries;
     const size_t q1 = static_cast<size_t>(nq) + 2;
     const uint32_t fl = spec->flags;
@@ -654,6 +668,7 @@ static int enqueue_dedup_walk(abb_graph *g, const abb_walk_spec *spec, const abb
     ENS(dd_sig, q1 * 8); ENS(dd_ssig, q1 * 8); ENS(dd_q, q1 * 4); ENS(dd_sq, q1 * 4); ENS(dd_head, q1); ENS(dd_gid, q1 * 8); ENS(dd_hp, q1 * 8);
     ENS(dd_glen, q1 * 8); ENS(dd_goff, q1 * 8); ENS(dd_arena, q1 * 4 * L1_CAP); ENS(dd_memoff, q1 * 8); ENS(dd_memsrc, q1 * 4); ENS(dd_memstate, q1 * 4);
     ENS(dd_indiv, q1 * 4); ENS(dd_cnt, 8 * sizeof(unsigned long long));
+    ENS(dd_lkey, q1 * 4); ENS(dd_lkey2, q1 * 4); ENS(dd_lgid, q1 * 4); ENS(dd_order, q1 * 4);
     ENS(dd_gstart, q1 * 8); ENS(dd_gcount, q1 * 4); ENS(dd_gmaxd, q1 * 4); ENS(dd_gflags, q1 * 4);
     if (fl & ABB_WALK_HIST) { ENS(dd_ghist, q1 * ABB_N_ENTITY_TYPES * 4); }
 #undef ENS
@@ -698,6 +713,17 @@ static int enqueue_dedup_walk(abb_graph *g, const abb_walk_spec *spec, const abb
     C.io.q_start = g->dd_gstart.as<int64_t>(); C.io.q_count = g->dd_gcount.as<int32_t>(); C.io.q_maxd = g->dd_gmaxd.as<int32_t>();
     C.io.q_flags = g->dd_gflags.as<int32_t>(); C.io.q_hist = g->dd_ghist.as<uint32_t>();
     C.qlist = nullptr; C.nq = 0; C.nq_dev = cnt;
+    if (g->locality_order) {
+        // walk order = first-seed order (a 2 M-key radix sort over the node-id bits, ~0.1 ms): neighbouring groups share rows in L2
+        uint32_t *lkey = g->dd_lkey.as<uint32_t>(), *lkey2 = g->dd_lkey2.as<uint32_t>();
+        int32_t *lgid = g->dd_lgid.as<int32_t>(), *order = g->dd_order.as<int32_t>();
+        dedup_locality_keys_kernel<<<blocks, 256, 0, st>>>(cnt, goff, g->dd_arena.as<int32_t>(), lkey, lgid, nq); g_launches++;
+        size_t t_ls = 0;
+        CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, t_ls, lkey, lkey2, lgid, order, static_cast<int>(nq), 0, 32, st));
+        if ((rc = g->dd_tmp.ensure(std::max(tmp, t_ls + 256)))) return rc;
+        CUDA_TRY(cub::DeviceRadixSort::SortPairs(g->dd_tmp.p, t_ls, lkey, lkey2, lgid, order, static_cast<int>(nq), 0, 32, st)); g_launches++;
+        C.qlist = order;
+    }
     C.depth_bias = 1; C.hist_roots = 1;
     C.mem_off = memoff; C.mem_src = g->dd_memsrc.as<int32_t>(); C.mem_state = g->dd_memstate.as<int32_t>();
     if ((rc = enqueue_tiers(g, C, nq, ctl, st))) return rc;
@@ -738,6 +764,7 @@ static int enqueue_walk(abb_graph *g, const abb_walk_spec *spec, const abb_walk_
 }
 
 extern "C" int abb_walk_launch(abb_graph *g, const abb_walk_spec *spec, const abb_walk_io *io, void *stream) {
+    NvtxRange nvtx_("abb_walk_launch");
     if (!g) return fail(ABB_ERR_ARG, "null graph");
     DeviceGuard dg(g->device);
     std::lock_guard<std::mutex> lk(g->mu);
@@ -955,6 +982,7 @@ static int walk_collect(abb_graph *g, const abb_walk_spec *spec, const abb_walk_
 
 extern "C" int abb_walk_host(abb_graph *g, const abb_walk_spec *spec, const int32_t *roots, const int64_t *root_off, const int32_t *targets,
                              int64_t n_queries, abb_walk_result **out) {
+    NvtxRange nvtx_("abb_walk_host");
     if (!g || !spec || !out || n_queries < 0 || (n_queries > 0 && !roots)) return fail(ABB_ERR_ARG, "bad arguments");
     if ((spec->flags & ABB_WALK_TARGET) && !targets) return fail(ABB_ERR_ARG, "TARGET needs targets");
     DeviceGuard dg(g->device);
@@ -998,6 +1026,7 @@ static unsigned warp_grid(const abb_graph *g, int64_t warps) {
 // Count pass of the exposure-path pipeline (paths.cuh): links -> unique vulnerable sources -> templates -> per-finding
 // row offsets.  Synchronises the stream twice to size the link / template buffers.
 static int enqueue_paths_count(abb_graph *g, const abb_paths_io *io, cudaStream_t st) {
+    NvtxRange nvtx_("paths: links / templates / offsets");
     if (!io || io->n_findings < 0 || !io->f_off || (io->n_findings && !io->findings)) return fail(ABB_ERR_ARG, "bad paths io");
     if (io->n_findings >= (1ll << 31) - 2) return fail(ABB_ERR_ARG, "too many findings in one batch");
     if (int rc = ensure_server_table(g, st)) return rc;
@@ -1073,6 +1102,7 @@ static int enqueue_paths_fill(abb_graph *g, const abb_paths_io *io, cudaStream_t
 }
 
 extern "C" int abb_paths_count_launch(abb_graph *g, const abb_paths_io *io, void *stream) {
+    NvtxRange nvtx_("abb_paths_count_launch");
     if (!g) return fail(ABB_ERR_ARG, "null graph");
     DeviceGuard dg(g->device);
     std::lock_guard<std::mutex> lk(g->mu);
@@ -1081,6 +1111,7 @@ extern "C" int abb_paths_count_launch(abb_graph *g, const abb_paths_io *io, void
     return enqueue_paths_count(g, io, st);
 }
 extern "C" int abb_paths_fill_launch(abb_graph *g, const abb_paths_io *io, void *stream) {
+    NvtxRange nvtx_("abb_paths_fill_launch");
     if (!g) return fail(ABB_ERR_ARG, "null graph");
     DeviceGuard dg(g->device);
     std::lock_guard<std::mutex> lk(g->mu);
@@ -1169,8 +1200,8 @@ extern "C" int64_t abb_paths_result_h2d_bytes(const abb_paths_result *r) { retur
 extern "C" int64_t abb_paths_result_d2h_bytes(const abb_paths_result *r) { return r->d2h; }
 
 // findings already on the device (d_findings) or staged from the host
-static int paths_run(abb_graph *g, const int32_t *h_findings, const int32_t *d_findings, int64_t nf, abb_paths_result **out) {
-    cudaStream_t st = g->stream;
+static int paths_run(abb_graph *g, const int32_t *h_findings, const int32_t *d_findings, int64_t nf, abb_paths_result **out, cudaStream_t st = nullptr) {
+    if (!st) st = g->stream;
     abb_paths_result *r = new abb_paths_result();
     r->nf = nf;
     if (!r->findings.alloc(static_cast<size_t>(nf + 1) * 4)) { abb_paths_result_free(r); return fail(ABB_ERR_NOMEM, "pinned host allocation failed"); }
@@ -1208,6 +1239,7 @@ static int paths_run(abb_graph *g, const int32_t *h_findings, const int32_t *d_f
 }
 
 extern "C" int abb_paths_host(abb_graph *g, const int32_t *findings, int64_t n_findings, abb_paths_result **out) {
+    NvtxRange nvtx_("abb_paths_host");
     if (!g || !out || n_findings < 0 || (n_findings && !findings)) return fail(ABB_ERR_ARG, "bad arguments");
     DeviceGuard dg(g->device);
     std::lock_guard<std::mutex> lk(g->mu);
@@ -1244,6 +1276,7 @@ struct ScopedDev {   // scoped device allocation for the ranking pass (sizes fol
 
 extern "C" int abb_paths_rank_host(abb_graph *g, const int32_t *findings, int64_t n_findings, const int32_t *base_id, const uint32_t *risk_rank, int64_t n_base,
                                    const int32_t *ncu, const int32_t *ntu, int64_t offset, int64_t limit, abb_rank_result **out) {
+    NvtxRange nvtx_("abb_paths_rank_host");
     if (!g || !out || n_findings < 0 || offset < 0 || limit < 0 || n_base <= 0 || !risk_rank || !ncu || !ntu || (n_findings && (!findings || !base_id)))
         return fail(ABB_ERR_ARG, "bad arguments");
     DeviceGuard dg(g->device);
@@ -1319,6 +1352,7 @@ extern "C" int abb_paths_rank_host(abb_graph *g, const int32_t *findings, int64_
 
 extern "C" int abb_exposure_host(abb_graph *g, const int32_t *findings, int64_t n_findings, int32_t max_depth, abb_walk_result **impact_out,
                                  abb_paths_result **paths_out) {
+    NvtxRange nvtx_("abb_exposure_host");
     if (!g || !impact_out || !paths_out || n_findings < 0 || (n_findings && !findings)) return fail(ABB_ERR_ARG, "bad arguments");
     DeviceGuard dg(g->device);
     std::lock_guard<std::mutex> lk(g->mu);
@@ -1326,23 +1360,35 @@ extern "C" int abb_exposure_host(abb_graph *g, const int32_t *findings, int64_t 
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
     const auto t0 = now();
+    // The exposure-path pipeline does not depend on the walk: it runs on its own stream, driven by a helper thread (its count pass
+    // synchronises that stream twice), while this thread stages and runs the walk.  The walk's node arena streams to the host over PCIe
+    // as it is produced (zero-copy); the path pipeline's kernels and its factorised result copy fit inside that window.
+    abb_paths_result *pr = nullptr;
+    int prc = ABB_OK;
+    std::string perr;
+    std::thread helper([&] {
+        DeviceGuard hdg(g->device);
+        prc = paths_run(g, findings, nullptr, n_findings, &pr, g->paths_stream);
+        if (prc) perr = g_err;
+    });
     abb_walk_spec spec = abb_spec_impact_of(max_depth);
     abb_walk_io io{}; unsigned long long totals[3] = {0, 0, 0}; int64_t h2d = 0;
     HostBlock direct;
-    if (int rc = walk_device_stage(g, &spec, findings, nullptr, nullptr, n_findings, &io, totals, &h2d, &direct)) { direct.release(); return rc; }
-    const auto t1 = now();
-    // result copies of the walk are enqueued (not waited for) before the path kernels; the findings are already resident
     abb_walk_result *wr = nullptr;
-    if (int rc = walk_collect(g, &spec, io, totals, h2d, &wr, false, &direct)) { direct.release(); return rc; }
+    int rc = walk_device_stage(g, &spec, findings, nullptr, nullptr, n_findings, &io, totals, &h2d, &direct);
+    const auto t1 = now();
+    if (!rc) rc = walk_collect(g, &spec, io, totals, h2d, &wr, true, &direct);
     direct.release();
     const auto t2 = now();
-    abb_paths_result *pr = nullptr;
-    int rc = paths_run(g, findings, g->d_roots.as<int32_t>(), n_findings, &pr);
-    cudaError_t ce = cudaStreamSynchronize(g->copy_stream);       // the walk's result copies overlapped the path pipeline
-    if (rc) { cudaStreamSynchronize(g->stream); abb_walk_result_free(wr); return rc; }
-    if (ce != cudaSuccess) { abb_walk_result_free(wr); abb_paths_result_free(pr); return fail(ABB_ERR_CUDA, "walk D2H failed: %s", cudaGetErrorString(ce)); }
+    helper.join();
     const auto t3 = now();
-    if (trace) fprintf(stderr, "[abb] exposure_host: stage+walk %.2f ms, enqueue result copies %.2f ms, paths (+ all copies) %.2f ms\n", ms(t0, t1), ms(t1, t2), ms(t2, t3));
+    if (rc || prc) {
+        if (wr) abb_walk_result_free(wr);
+        if (pr) abb_paths_result_free(pr);
+        if (!rc) { g_err = perr; return prc; }
+        return rc;
+    }
+    if (trace) fprintf(stderr, "[abb] exposure_host: stage+walk %.2f ms, result copies %.2f ms, wait for the path pipeline %.2f ms\n", ms(t0, t1), ms(t1, t2), ms(t2, t3));
     *impact_out = wr; *paths_out = pr;
     return ABB_OK;
 }

@@ -2,6 +2,7 @@
 // graph_backend.py:127-155.
 
 extern "C" int abb_bottleneck_host(abb_graph *g, const int32_t *sources, int64_t n_sources, uint64_t *scores_out) {
+    NvtxRange nvtx_("abb_bottleneck_host");
     if (!g || !scores_out || n_sources < 0 || (n_sources && !sources)) return fail(ABB_ERR_ARG, "bad arguments");
     DeviceGuard dg(g->device);
     std::lock_guard<std::mutex> lk(g->mu);

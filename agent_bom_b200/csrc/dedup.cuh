@@ -120,6 +120,16 @@ __global__ void dedup_roots_kernel(GraphView g, abb_walk_spec sp, const int32_t 
     for (int i = 0; i < n; i++) arena[o + i] = lst[i];
 }
 
+// per group: locality key = its first seed node (builder insertion order clusters an agent's servers / packages / credentials, so groups
+// with neighbouring seeds walk the same credential cliques); groups are then WALKED in key order so that those rows stay in L2
+__global__ void dedup_locality_keys_kernel(const unsigned long long *counters, const int64_t *goff, const int32_t *arena, uint32_t *key, int32_t *gid, int64_t cap) {
+    const int64_t gi = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (gi >= cap) return;
+    const int64_t ng = static_cast<int64_t>(counters[0]);
+    gid[gi] = static_cast<int32_t>(gi);
+    key[gi] = (gi < ng && goff[gi + 1] > goff[gi]) ? static_cast<uint32_t>(arena[goff[gi]]) : 0xFFFFFFFFu;   // padding sorts last and is never read (count = n_groups)
+}
+
 // per eligible member: its group id (for the share pass), its source, and exact verification of its list against
 // the group's (signature collisions are sent to the individual list)
 __global__ void dedup_members_kernel(GraphView g, abb_walk_spec sp, const int32_t *roots, const int32_t *sq, const uint8_t *head, const int64_t *gid_incl,

@@ -17,6 +17,7 @@ extern "C" double abb_lateral_result_ms(const abb_lateral_result *r) { return r-
 extern "C" int abb_lateral_paths_host(int device, int32_t n_nodes, const int64_t *adj_off, const int32_t *adj_nbr, const uint8_t *adj_kind,
                                       const uint8_t *node_kind, const int32_t *node_key, int64_t n_sources, const int32_t *sources,
                                       const int32_t *source_key, int32_t max_depth, int64_t max_pops, abb_lateral_result **out) {
+    NvtxRange nvtx_("abb_lateral_paths_host");
     if (!out || n_nodes < 0 || n_sources < 0 || !adj_off || (n_nodes && (!node_kind || !node_key)) || (n_sources && (!sources || !source_key)))
         return fail(ABB_ERR_ARG, "bad arguments");
     if (max_depth < 0 || max_depth + 2 > LAT_MAX_W) return fail(ABB_ERR_ARG, "max_depth must be 0..%d", LAT_MAX_W - 2);

@@ -73,6 +73,7 @@ static int exclusive_scan_i64(cudaStream_t st, const int64_t *in, int64_t *out, 
 
 extern "C" int abb_dependency_reach_host(abb_graph *g, const int32_t *agents, int64_t n_agents, uint32_t rel_mask, uint32_t vuln_pkg_mask,
                                          abb_reach_result **out) {
+    NvtxRange nvtx_("abb_dependency_reach_host");
     if (!g || !out || n_agents < 0 || (n_agents && !agents)) return fail(ABB_ERR_ARG, "bad arguments");
     DeviceGuard dg(g->device);
     std::lock_guard<std::mutex> lk(g->mu);

@@ -24,6 +24,7 @@ struct StreamGuard {
 
 extern "C" int abb_group_union_host(int device, int64_t n_groups, const int64_t *member_off, const int32_t *members, int64_t n_members,
                                     const int64_t *item_off, const int32_t *items, const uint8_t *w0, const uint8_t *w1, abb_union_result **out) {
+    NvtxRange nvtx_("abb_group_union_host");
     if (!out || n_groups < 0 || n_members < 0 || !member_off || !item_off) return fail(ABB_ERR_ARG, "bad arguments");
     if (n_groups >= (1ll << 31)) return fail(ABB_ERR_ARG, "at most 2^31-1 groups");
     const int64_t n_refs = member_off[n_groups], n_items = item_off[n_members];

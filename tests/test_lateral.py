@@ -125,3 +125,29 @@ def test_device_search_against_the_oracle_where_the_caps_bite():
     assert got == [[], []] and lo.search(lone, "agent:x", 5) == []
     with pytest.raises(Exception):
         search_many(lone, ["agent:x"], 9)                                    # max_depth beyond the record width is refused, not truncated
+
+
+def test_adjacency_encoding_is_cached_per_graph_and_rebuilt_on_change():
+    """The array encoding of ``graph.adjacency`` (the >99 % of a call that was Python) is reused while the graph is unchanged."""
+    from types import SimpleNamespace as NS
+
+    from agent_bom_b200 import lateral
+
+    class G:
+        pass
+
+    g = G()
+    g.nodes = {f"agent:{i}": NS(kind="agent", label=f"a{i}", metadata={}) for i in range(4)}
+    g.edges = []
+    g.adjacency = {"agent:0": [NS(target="agent:1", kind="shares_server")], "agent:1": [NS(target="agent:2", kind="shares_server")]}
+    a1 = lateral._arrays_for(g)
+    assert lateral._arrays_for(g) is a1
+    g.adjacency["agent:2"] = [NS(target="agent:3", kind="shares_credential")]
+    a2 = lateral._arrays_for(g)
+    assert a2 is not a1 and len(a2.nbr) == 3 and lateral._arrays_for(g) is a2
+    key = id(g)
+    del g, a1, a2
+    import gc
+
+    gc.collect()
+    assert key not in lateral._ARRAYS_CACHE
