@@ -104,6 +104,7 @@ EXPORTS = {
     "abb_walk_result_estart": (vp, [vp]),
     "abb_walk_result_ecount": (vp, [vp]),
     "abb_walk_result_hist": (vp, [vp]),
+    "abb_walk_result_hist_packed": (vp, [vp, vp, vp]),
     "abb_walk_result_nodes": (vp, [vp]),
     "abb_walk_result_parent": (vp, [vp]),
     "abb_walk_result_depth": (vp, [vp]),

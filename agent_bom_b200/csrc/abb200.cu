@@ -23,6 +23,7 @@
 #include "../../include/abb200.h"
 #include "dedup.cuh"
 #include "paths.cuh"
+#include "histpack.cuh"
 #include "reach.cuh"
 #include "union.cuh"
 #include "centrality.cuh"
@@ -214,6 +215,10 @@ struct abb_graph {
     bool dedup_enabled = true;
     int slice_align = 0;        // set while a host-mapped arena is the walk target
     bool align_direct = true;
+    bool hist_pack = true;      // host results carry only the non-zero histogram columns at the narrowest width (histpack.cuh)
+    DevBuf d_histinfo, d_hist_packed;
+    unsigned long long hist_info[2] = {0, 0};   // column mask, largest count of the walk just staged
+    bool hist_info_valid = false;
     bool zero_copy = true;      // host-API walks write the node arena straight into pinned host memory when its size is known
     int64_t last_walk_queries = 0;
     bool last_walk_dedup = false;
@@ -288,6 +293,7 @@ static int graph_finish_init(abb_graph *g) {
     if (const char *e = getenv("ABB_MID_WARPS")) g->mid_warps = atoi(e) == 4 ? 4 : 8;
     if (const char *e = getenv("ABB_S1_MINB")) g->s1_minb = atoi(e) == 4 ? 4 : 5;
     if (const char *e = getenv("ABB_ZEROCOPY")) g->zero_copy = atoi(e) != 0;
+    if (const char *e = getenv("ABB_HIST_PACK")) g->hist_pack = atoi(e) != 0;
     if (const char *e = getenv("ABB_ALIGN_DIRECT")) g->align_direct = atoi(e) != 0;
     if (!g->v.rank) {
         if (int rc = g->identity_rank.ensure(static_cast<size_t>(n + 1) * 4)) return rc;
@@ -395,6 +401,7 @@ extern "C" int abb_graph_set_option(abb_graph *g, const char *name, int64_t valu
         if (value < 32 || value > 36864) return fail(ABB_ERR_ARG, "big_qcap must be in [32, 36864]");
         g->big_qcap = static_cast<int>(value);
     } else if (k == "zero_copy") g->zero_copy = value != 0;
+    else if (k == "hist_pack") g->hist_pack = value != 0;
     else if (k == "big_limit") {
         if (value < 0) return fail(ABB_ERR_ARG, "big_limit must be >= 0");
         g->big_limit = value;
@@ -409,6 +416,7 @@ extern "C" int64_t abb_graph_get_option(const abb_graph *g, const char *name) {
     if (k == "mid_qcap") return g->mid_qcap;
     if (k == "big_qcap") return g->big_qcap;
     if (k == "zero_copy") return g->zero_copy;
+    if (k == "hist_pack") return g->hist_pack;
     if (k == "big_limit") return g->big_limit;
     return -1;
 }
@@ -422,7 +430,7 @@ extern "C" void abb_graph_free(abb_graph *g) {
     if (g->paths_stream) { cudaStreamSynchronize(g->paths_stream); cudaStreamDestroy(g->paths_stream); }
     if (g->ev_copy) cudaEventDestroy(g->ev_copy);
     for (auto &e : g->ev) if (e) cudaEventDestroy(e);
-    for (DevBuf *b : {&g->ctl, &g->ov1, &g->ov2, &g->ov3, &g->ov4, &g->b_gq, &g->b_gpar, &g->b_gdep, &g->g_bitmap, &g->g_queue, &g->g_par, &g->g_dep, &g->x_bitmap, &g->x_queue, &g->x_par, &g->x_dep, &g->dd_sig, &g->dd_ssig, &g->dd_q, &g->dd_sq, &g->dd_head, &g->dd_gid, &g->dd_hp, &g->dd_glen, &g->dd_goff, &g->dd_arena, &g->dd_memoff, &g->dd_memsrc, &g->dd_memstate, &g->dd_indiv, &g->dd_cnt, &g->dd_tmp, &g->dd_lkey, &g->dd_lkey2, &g->dd_lgid, &g->dd_order, &g->dd_gstart, &g->dd_gcount, &g->dd_gmaxd, &g->dd_gflags, &g->dd_ghist, &g->identity_rank, &g->d_roots, &g->d_root_off,
+    for (DevBuf *b : {&g->ctl, &g->ov1, &g->ov2, &g->ov3, &g->ov4, &g->b_gq, &g->b_gpar, &g->b_gdep, &g->g_bitmap, &g->g_queue, &g->g_par, &g->g_dep, &g->x_bitmap, &g->x_queue, &g->x_par, &g->x_dep, &g->dd_sig, &g->dd_ssig, &g->dd_q, &g->dd_sq, &g->dd_head, &g->dd_gid, &g->dd_hp, &g->dd_glen, &g->dd_goff, &g->dd_arena, &g->dd_memoff, &g->dd_memsrc, &g->dd_memstate, &g->dd_indiv, &g->dd_cnt, &g->dd_tmp, &g->dd_lkey, &g->dd_lkey2, &g->dd_lgid, &g->dd_order, &g->dd_gstart, &g->dd_gcount, &g->dd_gmaxd, &g->dd_gflags, &g->dd_ghist, &g->d_histinfo, &g->d_hist_packed, &g->identity_rank, &g->d_roots, &g->d_root_off,
                       &g->d_targets, &g->d_qstart, &g->d_qcount, &g->d_qmaxd, &g->d_qflags, &g->d_qestart, &g->d_qecount, &g->d_qhist, &g->d_nodes,
                       &g->d_parent, &g->d_depth, &g->d_edges, &g->d_totals, &g->p_findings, &g->p_counts, &g->p_off, &g->p_hops, &g->p_rels,
                       &g->p_ncred, &g->p_ntool, &g->p_scan_tmp, &g->srv_cred, &g->srv_tool, &g->pl_cnt, &g->pl_off, &g->pl_vs, &g->pl_rel, &g->pl_rows, &g->pl_roff, &g->pl_toff, &g->pl_need, &g->pl_ulist, &g->pl_nu, &g->pt_cnt, &g->pt_off, &g->pt_off_node, &g->pt_cnt_node, &g->pt_row, &g->pt_rel})
@@ -838,11 +846,16 @@ struct abb_walk_result {
     int64_t nq = 0, total_nodes = 0, total_edges = 0, h2d = 0, d2h = 0;
     uint32_t flags = 0;
     HostBlock q_start, q_count, q_maxd, q_flags, q_estart, q_ecount, q_hist, nodes, parent, depth, edges;
+    // histograms as shipped: k non-zero columns (bit set in hist_mask) of hist_width bytes per count; q_hist is rebuilt from it on demand
+    HostBlock q_hist_packed;
+    bool hist_is_packed = false, hist_expanded = false;
+    uint32_t hist_mask = 0; int hist_k = 0, hist_width = 0;
+    std::mutex mu;
 };
 
 extern "C" void abb_walk_result_free(abb_walk_result *r) {
     if (!r) return;
-    for (HostBlock *b : {&r->q_start, &r->q_count, &r->q_maxd, &r->q_flags, &r->q_estart, &r->q_ecount, &r->q_hist, &r->nodes, &r->parent, &r->depth, &r->edges})
+    for (HostBlock *b : {&r->q_start, &r->q_count, &r->q_maxd, &r->q_flags, &r->q_estart, &r->q_ecount, &r->q_hist, &r->q_hist_packed, &r->nodes, &r->parent, &r->depth, &r->edges})
         b->release();
     delete r;
 }
@@ -855,7 +868,47 @@ extern "C" const int32_t *abb_walk_result_maxd(const abb_walk_result *r) { retur
 extern "C" const int32_t *abb_walk_result_flags(const abb_walk_result *r) { return r->q_flags.as<int32_t>(); }
 extern "C" const int64_t *abb_walk_result_estart(const abb_walk_result *r) { return r->q_estart.as<int64_t>(); }
 extern "C" const int64_t *abb_walk_result_ecount(const abb_walk_result *r) { return r->q_ecount.as<int64_t>(); }
-extern "C" const uint32_t *abb_walk_result_hist(const abb_walk_result *r) { return r->q_hist.as<uint32_t>(); }
+// packed columns -> the dense [nq x ABB_N_ENTITY_TYPES] uint32 table, once, threads over query ranges
+static bool hist_expand(abb_walk_result *r) {
+    std::lock_guard<std::mutex> lk(r->mu);
+    if (!r->hist_is_packed || r->hist_expanded) return true;
+    const size_t q = static_cast<size_t>(r->nq);
+    if (!r->q_hist.alloc(q * ABB_N_ENTITY_TYPES * 4 + 4)) return false;
+    uint32_t *dense = r->q_hist.as<uint32_t>();
+    int col[ABB_N_ENTITY_TYPES]; int k = 0;
+    for (int t = 0; t < ABB_N_ENTITY_TYPES; t++) if (r->hist_mask >> t & 1u) col[k++] = t;
+    const void *packed = r->q_hist_packed.p;
+    const int width = r->hist_width;
+    auto work = [&](size_t a, size_t b) {
+        memset(dense + a * ABB_N_ENTITY_TYPES, 0, (b - a) * ABB_N_ENTITY_TYPES * 4);
+        if (width == 2) {
+            const uint16_t *src = static_cast<const uint16_t *>(packed);
+            for (size_t i = a; i < b; i++) for (int j = 0; j < k; j++) dense[i * ABB_N_ENTITY_TYPES + col[j]] = src[i * k + j];
+        } else {
+            const uint32_t *src = static_cast<const uint32_t *>(packed);
+            for (size_t i = a; i < b; i++) for (int j = 0; j < k; j++) dense[i * ABB_N_ENTITY_TYPES + col[j]] = src[i * k + j];
+        }
+    };
+    const size_t nthreads = std::max<size_t>(1, std::min<size_t>(16, q / (1 << 17)));
+    if (nthreads <= 1) work(0, q);
+    else {
+        std::vector<std::thread> th;
+        for (size_t t = 0; t < nthreads; t++) th.emplace_back(work, q * t / nthreads, q * (t + 1) / nthreads);
+        for (auto &x : th) x.join();
+    }
+    r->hist_expanded = true;
+    return true;
+}
+extern "C" const uint32_t *abb_walk_result_hist(const abb_walk_result *r) {
+    if (!(r->flags & ABB_WALK_HIST)) return nullptr;
+    return hist_expand(const_cast<abb_walk_result *>(r)) ? r->q_hist.as<uint32_t>() : nullptr;
+}
+extern "C" const void *abb_walk_result_hist_packed(const abb_walk_result *r, uint32_t *columns_mask, int32_t *bytes_per_count) {
+    if (!r || !r->hist_is_packed) return nullptr;
+    if (columns_mask) *columns_mask = r->hist_mask;
+    if (bytes_per_count) *bytes_per_count = r->hist_width;
+    return r->q_hist_packed.p ? r->q_hist_packed.p : static_cast<const void *>(r->q_start.p);   // k == 0: nothing to read, but not NULL
+}
 extern "C" const int32_t *abb_walk_result_nodes(const abb_walk_result *r) { return r->nodes.as<int32_t>(); }
 extern "C" const int32_t *abb_walk_result_parent(const abb_walk_result *r) { return r->parent.as<int32_t>(); }
 extern "C" const int32_t *abb_walk_result_depth(const abb_walk_result *r) { return r->depth.as<int32_t>(); }
@@ -871,6 +924,7 @@ static int walk_device_stage(abb_graph *g, const abb_walk_spec *spec, const int3
                              int64_t nq, abb_walk_io *io_out, unsigned long long (&totals)[3], int64_t *h2d, HostBlock *direct_nodes = nullptr) {
     cudaStream_t st = g->stream;
     const uint32_t fl = spec->flags;
+    g->hist_info_valid = false;
     const int64_t n_roots = root_off ? root_off[nq] : nq;
     if (n_roots < 0) return fail(ABB_ERR_ARG, "bad root_off");
     const size_t q1 = static_cast<size_t>(nq) + 1;
@@ -919,8 +973,17 @@ static int walk_device_stage(abb_graph *g, const abb_walk_spec *spec, const int3
         if (erc) return erc;
         CUDA_TRY(cudaEventRecord(g->ev[1], st));
         g->walk_timed = true;
+        const bool scan_hist = (fl & ABB_WALK_HIST) && g->hist_pack && nq >= 1024;
+        if (scan_hist) {
+            if (int rc = g->d_histinfo.ensure(2 * sizeof(unsigned long long))) return rc;
+            CUDA_TRY(cudaMemsetAsync(g->d_histinfo.p, 0, 2 * sizeof(unsigned long long), st));
+            hist_columns_kernel<<<static_cast<unsigned>(g->sm_count) * 8, 256, 0, st>>>(io.q_hist, nq * ABB_N_ENTITY_TYPES, g->d_histinfo.as<unsigned long long>());
+            g_launches++;
+            CUDA_TRY(cudaMemcpyAsync(g->hist_info, g->d_histinfo.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        }
         CUDA_TRY(cudaMemcpyAsync(totals, g->d_totals.p, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
+        g->hist_info_valid = scan_hist;
         unsigned long long fatal = 0, fatal2 = 0;
         CUDA_TRY(cudaMemcpy(&fatal, g->ctl.as<unsigned long long>() + CTL_FATAL, sizeof fatal, cudaMemcpyDeviceToHost));
         CUDA_TRY(cudaMemcpy(&fatal2, g->ctl.as<unsigned long long>() + CTL_SET + CTL_FATAL, sizeof fatal2, cudaMemcpyDeviceToHost));
@@ -958,7 +1021,17 @@ static int walk_collect(abb_graph *g, const abb_walk_spec *spec, const abb_walk_
     if (have_nodes) { r->nodes = *direct_nodes; direct_nodes->p = nullptr; direct_nodes->bytes = 0; }
     bool ok = r->q_start.alloc(q * 8) && r->q_count.alloc(q * 4) && r->q_maxd.alloc(q * 4) && r->q_flags.alloc(q * 4) && (have_nodes || r->nodes.alloc(tn * 4));
     if (fl & ABB_WALK_EDGES) ok = ok && r->q_estart.alloc(q * 8) && r->q_ecount.alloc(q * 8) && r->edges.alloc(te * 4);
-    if (fl & ABB_WALK_HIST) ok = ok && r->q_hist.alloc(q * ABB_N_ENTITY_TYPES * 4);
+    const bool pack = (fl & ABB_WALK_HIST) && g->hist_info_valid;
+    g->hist_info_valid = false;
+    HistCols hc{};
+    if (pack) {
+        r->hist_is_packed = true;
+        r->hist_mask = static_cast<uint32_t>(g->hist_info[0]);
+        for (int t = 0; t < ABB_N_ENTITY_TYPES; t++) if (r->hist_mask >> t & 1u) hc.col[hc.k++] = static_cast<uint8_t>(t);
+        r->hist_k = hc.k;
+        r->hist_width = g->hist_info[1] < 65536ull ? 2 : 4;
+        ok = ok && (hc.k == 0 || r->q_hist_packed.alloc(q * hc.k * r->hist_width));
+    } else if (fl & ABB_WALK_HIST) ok = ok && r->q_hist.alloc(q * ABB_N_ENTITY_TYPES * 4);
     if (fl & ABB_WALK_PARENTS) ok = ok && r->parent.alloc(tn * 4);
     if (fl & ABB_WALK_DEPTHS) ok = ok && r->depth.alloc(tn * 4);
     if (!ok) { abb_walk_result_free(r); return fail(ABB_ERR_NOMEM, "pinned host allocation failed"); }
@@ -971,7 +1044,18 @@ static int walk_collect(abb_graph *g, const abb_walk_spec *spec, const abb_walk_
     acc(d2h(r->q_start, io.q_start, q * 8)); acc(d2h(r->q_count, io.q_count, q * 4)); acc(d2h(r->q_maxd, io.q_maxd, q * 4)); acc(d2h(r->q_flags, io.q_flags, q * 4));
     if (have_nodes) r->d2h += static_cast<int64_t>((totals[2] ? totals[2] : static_cast<unsigned long long>(tn)) * 4); else acc(d2h(r->nodes, io.nodes, tn * 4));
     if (fl & ABB_WALK_EDGES) { acc(d2h(r->q_estart, io.q_estart, q * 8)); acc(d2h(r->q_ecount, io.q_ecount, q * 8)); acc(d2h(r->edges, io.edges, te * 4)); }
-    if (fl & ABB_WALK_HIST) acc(d2h(r->q_hist, io.q_hist, q * ABB_N_ENTITY_TYPES * 4));
+    if (pack) {
+        if (hc.k) {
+            const size_t pbytes = q * hc.k * r->hist_width;
+            if (int rc = g->d_hist_packed.ensure(pbytes)) { abb_walk_result_free(r); return rc; }
+            const unsigned grid = static_cast<unsigned>(g->sm_count) * 8;
+            if (r->hist_width == 2) hist_pack_kernel<uint16_t><<<grid, 256, 0, st>>>(io.q_hist, nq, hc, g->d_hist_packed.as<uint16_t>());
+            else hist_pack_kernel<uint32_t><<<grid, 256, 0, st>>>(io.q_hist, nq, hc, g->d_hist_packed.as<uint32_t>());
+            g_launches++;
+            acc(cudaGetLastError());
+            acc(d2h(r->q_hist_packed, g->d_hist_packed.p, pbytes));
+        }
+    } else if (fl & ABB_WALK_HIST) acc(d2h(r->q_hist, io.q_hist, q * ABB_N_ENTITY_TYPES * 4));
     if (fl & ABB_WALK_PARENTS) acc(d2h(r->parent, io.parent, tn * 4));
     if (fl & ABB_WALK_DEPTHS) acc(d2h(r->depth, io.depth, tn * 4));
     if (e == cudaSuccess && sync) e = cudaStreamSynchronize(st);

@@ -67,13 +67,30 @@ class WalkResult:
     nodes: np.ndarray
     parent: np.ndarray | None = None
     depth: np.ndarray | None = None
-    hist: np.ndarray | None = None
     estart: np.ndarray | None = None
     ecount: np.ndarray | None = None
     edges: np.ndarray | None = None
     h2d_bytes: int = 0
     d2h_bytes: int = 0
     kernel_ms: float = 0.0
+    # entity-type histograms as they crossed PCIe: the columns that are non-zero somewhere in the batch (``hist_cols``), uint16 unless a
+    # count needs more; ``hist`` is the dense [n_queries, N_ENTITY_TYPES] uint32 table, built on first access
+    hist_packed: np.ndarray | None = None
+    hist_cols: np.ndarray | None = None
+    _hist: np.ndarray | None = None
+
+    @property
+    def hist(self) -> np.ndarray | None:
+        if self._hist is None and self.hist_packed is not None:
+            dense = np.zeros((len(self), N_ENTITY_TYPES), np.uint32)
+            if self.hist_cols.size:
+                dense[:, self.hist_cols] = self.hist_packed
+            self._hist = dense
+        return self._hist
+
+    @hist.setter
+    def hist(self, value) -> None:
+        self._hist = value
 
     def __len__(self) -> int:
         return int(self.count.shape[0])
@@ -91,6 +108,8 @@ class WalkResult:
         return self.edges[s: s + int(self.ecount[q])]
 
     def hist_dict(self, q: int) -> dict[str, int]:
+        if self._hist is None and self.hist_packed is not None:
+            return {ENTITY_VALUES[int(t)]: int(c) for t, c in zip(self.hist_cols, self.hist_packed[q]) if c}
         return {ENTITY_VALUES[t]: int(c) for t, c in enumerate(self.hist[q]) if c}
 
 
@@ -287,7 +306,15 @@ class DeviceGraph:
         if flags & _lib.WALK_DEPTHS:
             out.depth = _view(lib.abb_walk_result_depth(res), tn, np.int32, owner)
         if flags & _lib.WALK_HIST:
-            out.hist = _view(lib.abb_walk_result_hist(res), nq * N_ENTITY_TYPES, np.uint32, owner).reshape(nq, N_ENTITY_TYPES)
+            mask, width = C.c_uint32(0), C.c_int32(0)
+            packed = lib.abb_walk_result_hist_packed(res, C.byref(mask), C.byref(width))
+            if packed:
+                cols = np.array([t for t in range(N_ENTITY_TYPES) if mask.value >> t & 1], dtype=np.int64)
+                out.hist_cols = cols
+                dt = np.uint16 if width.value == 2 else np.uint32
+                out.hist_packed = (_view(packed, nq * len(cols), dt, owner) if len(cols) else np.zeros(0, dt)).reshape(nq, len(cols))
+            else:
+                out.hist = _view(lib.abb_walk_result_hist(res), nq * N_ENTITY_TYPES, np.uint32, owner).reshape(nq, N_ENTITY_TYPES)
         if flags & _lib.WALK_EDGES:
             out.estart = _view(lib.abb_walk_result_estart(res), nq, np.int64, owner)
             out.ecount = _view(lib.abb_walk_result_ecount(res), nq, np.int64, owner)

@@ -58,6 +58,24 @@ LATERAL = (1 << 13) | (1 << 14) | (1 << 15)                   # lateral set (con
 MASKS = (("all", 0, False), ("reach4", REACH4, False), ("lateral", LATERAL, False), ("static_only", 0, True))
 
 
+_JSON_OUT = None
+
+
+def claim_stdout() -> None:
+    """Keep the process's real stdout for the ONE JSON line: file descriptor 1 is pointed at stderr for everything else
+    (NCCL's version banner, library chatter of child threads), the JSON line goes to a duplicate of the original."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    out = _JSON_OUT or sys.stdout
+    print(json.dumps(line), file=out, flush=True)
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
@@ -247,7 +265,7 @@ def run_reference(args) -> int:
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -324,6 +342,7 @@ def main() -> int:
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -604,7 +623,7 @@ def main() -> int:
         if mode == "enumerate":
             line["enumerate"] = {"per_walk_ms": extra_ms, "emitted_per_step_rank0": {k: {"nodes": v[0], "edges": v[1]} for k, v in extra_tot.items()},
                                  "unit_of_work": "impact_of + exposure paths + bfs(depth 4, traversable_only) + traverse_subgraph(depth 4) x {all, reach4, lateral, static_only} per finding"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     abdist.barrier(info)
     if info.world > 1:
         import torch.distributed as tdist

@@ -238,6 +238,12 @@ const int32_t *abb_walk_result_flags(const abb_walk_result *r);
 const int64_t *abb_walk_result_estart(const abb_walk_result *r);
 const int64_t *abb_walk_result_ecount(const abb_walk_result *r);
 const uint32_t *abb_walk_result_hist(const abb_walk_result *r);
+/* Histograms as they crossed PCIe (batches of >= 1024 queries, option "hist_pack", default on): only the entity-type columns
+ * that are non-zero somewhere in the batch (bit t of *columns_mask = column t, ascending), row-major [n_queries x popcount(mask)],
+ * counts of *bytes_per_count bytes (2 unless a count exceeds 65 535, else 4).  This is the reference's `affected_by_type`
+ * (graph/container.py:268-276: a dict holding only the types present).  abb_walk_result_hist rebuilds the dense
+ * [n_queries x ABB_N_ENTITY_TYPES] uint32 table from it on first call.  Returns NULL when the result holds the dense table. */
+const void *abb_walk_result_hist_packed(const abb_walk_result *r, uint32_t *columns_mask, int32_t *bytes_per_count);
 const int32_t *abb_walk_result_nodes(const abb_walk_result *r);
 const int32_t *abb_walk_result_parent(const abb_walk_result *r);
 const int32_t *abb_walk_result_depth(const abb_walk_result *r);

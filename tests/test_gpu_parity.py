@@ -279,6 +279,24 @@ def test_dependency_reach(key):
         np.testing.assert_array_equal(got[k], want[k], err_msg=k)
 
 
+@pytest.mark.parametrize("key", [SEEDED[2], "mesh_inventory", "estate_dense_40"])
+def test_dependency_reach_device_merge_of_agent_shards(key):
+    """a9 across ranks: per-shard device results merged by the CUDA path of dist.merge_dependency_reach (64-bit key sort on the
+    device) == the numpy merge == the unsplit call."""
+    from agent_bom_b200.dist import REACH_KEYS, merge_dependency_reach
+
+    og, dg, nt, rank, _ = graphs_for(key)
+    agents = np.flatnonzero(nt == 0).astype(np.int32)
+    whole = dg.dependency_reach(agents, REACH4, VULN_PKG)
+    for cuts in ([0, len(agents) // 2, len(agents)], [0, 1, len(agents) // 3, len(agents) // 3, len(agents)]):
+        parts = [dg.dependency_reach(agents[a:b], REACH4, VULN_PKG) for a, b in zip(cuts, cuts[1:])]
+        on_device = merge_dependency_reach(parts, rank, "cuda:0")
+        on_host = merge_dependency_reach(parts, rank)
+        for k in REACH_KEYS:
+            np.testing.assert_array_equal(np.asarray(on_device[k]), np.asarray(whole[k]), err_msg=k)
+            np.testing.assert_array_equal(np.asarray(on_host[k]), np.asarray(whole[k]), err_msg=k)
+
+
 def test_exposure_many_matches_separate_calls():
     og, dg, nt, _, _ = graphs_for("estate_dense_40")
     findings = np.flatnonzero((nt == 8) | (nt == 9)).astype(np.int32)
