@@ -183,12 +183,13 @@ def barrier(info: RankInfo) -> None:
 REACH_KEYS = ("pkg_ids", "pkg_off", "pkg_agents", "pkg_minhop", "vuln_ids", "vuln_poff", "vuln_pkgs", "vuln_aoff", "vuln_agents", "vuln_minhop")
 
 
-def all_gather_ragged(arr: np.ndarray, info: RankInfo, device: torch.device | str) -> list[np.ndarray]:
-    """Every rank's 1-D array on every rank: one size exchange, one padded all-gather (NCCL over NVLink on GPUs, gloo on CPU)."""
+def all_gather_ragged(arr: np.ndarray, info: RankInfo, device: torch.device | str, keep_on_device: bool = False) -> list:
+    """Every rank's 1-D array on every rank: one size exchange, one padded all-gather (NCCL over NVLink on GPUs, gloo on CPU).
+    ``keep_on_device`` returns the parts as tensors on ``device`` (for a merge that runs there) instead of numpy arrays."""
     a = np.ascontiguousarray(arr)
-    if info.world == 1:
-        return [a]
     device = torch.device(device)
+    if info.world == 1:
+        return [torch.from_numpy(a).to(device)] if keep_on_device else [a]
     size = torch.tensor([a.shape[0]], dtype=torch.int64, device=device)
     sizes = [torch.zeros_like(size) for _ in range(info.world)]
     dist.all_gather(sizes, size)
@@ -199,7 +200,13 @@ def all_gather_ragged(arr: np.ndarray, info: RankInfo, device: torch.device | st
         buf[: a.shape[0]] = torch.from_numpy(a).to(device)
     parts = [torch.empty_like(buf) for _ in range(info.world)]
     dist.all_gather(parts, buf)
+    if keep_on_device:
+        return [p[:c] for p, c in zip(parts, counts)]
     return [p[:c].cpu().numpy() for p, c in zip(parts, counts)]
+
+
+def _host(x) -> np.ndarray:
+    return x.cpu().numpy() if torch.is_tensor(x) else np.asarray(x)
 
 
 def merge_dependency_reach(partials: list[dict], node_rank, device: torch.device | str | None = None) -> dict:
@@ -225,10 +232,10 @@ def merge_dependency_reach(partials: list[dict], node_rank, device: torch.device
         big = np.full(n_groups, np.iinfo(np.int32).max, dtype=np.int64)
         all_counts = []
         for p in partials:
-            counts = np.diff(np.asarray(p[key_off], dtype=np.int64))
+            counts = np.diff(_host(p[key_off]).astype(np.int64))
             all_counts.append(counts)
             reached = counts > 0
-            big[reached] = np.minimum(big[reached], np.asarray(p[key_min], dtype=np.int64)[reached])
+            big[reached] = np.minimum(big[reached], _host(p[key_min]).astype(np.int64)[reached])
         total = np.sum(all_counts, axis=0) if all_counts else np.zeros(n_groups, np.int64)
         off = np.zeros(n_groups + 1, dtype=np.int64)
         off[1:] = np.cumsum(total)
@@ -236,7 +243,7 @@ def merge_dependency_reach(partials: list[dict], node_rank, device: torch.device
             keys, items = [], []
             gid = torch.arange(n_groups, dtype=torch.int64, device=dev)
             for p, counts in zip(partials, all_counts):
-                itm = torch.from_numpy(np.ascontiguousarray(p[key_items], dtype=np.int32)).to(dev)
+                itm = p[key_items].to(dev) if torch.is_tensor(p[key_items]) else torch.from_numpy(np.ascontiguousarray(p[key_items], dtype=np.int32)).to(dev)
                 grp = torch.repeat_interleave(gid, torch.from_numpy(counts).to(dev), output_size=int(itm.shape[0]))
                 keys.append(grp * span + rank_t[itm.long()])
                 items.append(itm)
@@ -247,28 +254,48 @@ def merge_dependency_reach(partials: list[dict], node_rank, device: torch.device
                 merged = np.zeros(0, np.int32)
         else:
             grp = np.concatenate([np.repeat(np.arange(n_groups, dtype=np.int64), c) for c in all_counts]) if all_counts else np.zeros(0, np.int64)
-            itm = np.concatenate([np.asarray(p[key_items], dtype=np.int32) for p in partials]) if partials else np.zeros(0, np.int32)
+            itm = np.concatenate([_host(p[key_items]).astype(np.int32, copy=False) for p in partials]) if partials else np.zeros(0, np.int32)
             merged = itm[np.lexsort((node_rank[itm], grp))]
         out[key_off], out[key_items] = off, merged
         out[key_min] = np.where(big == np.iinfo(np.int32).max, 0, big).astype(np.int32)
     return out
 
 
-def dependency_reach_sharded(local_reach, agents, node_rank, info: RankInfo, device: torch.device | str) -> dict:
+def dependency_reach_sharded(local_reach, agents, node_rank, info: RankInfo, device: torch.device | str, stats: dict | None = None) -> dict:
     """``compute_dependency_reach`` with the agent BFSs split across ranks.
 
     ``local_reach(agent_shard) -> dict`` is this rank's device call (``lambda a: dg.dependency_reach(a, REACH_MASK,
     VULN_PKG_MASK)``).  Pass 1 (a BFS per agent) needs no communication; pass 2's per-package union / minimum is the
-    exchange: every rank's ragged agent lists are all-gathered and merged, so every rank ends with the full answer."""
+    exchange: every rank's ragged agent lists are all-gathered and merged, so every rank ends with the full answer.
+    On GPUs the gathered lists stay on the device and are merged there.  ``stats`` (optional) receives the wall-clock seconds of
+    the three phases on this rank: ``local_s``, ``gather_s``, ``merge_s``."""
+    import time
+
+    def mark():
+        if torch.device(device).type == "cuda":
+            torch.cuda.synchronize(device)
+        return time.perf_counter()
+
     agents = np.ascontiguousarray(agents, dtype=np.int32)
     lo, hi = shard_bounds(len(agents), info.world, info.rank)
+    t0 = mark()
     mine = local_reach(agents[lo:hi])
+    t1 = mark()
     if info.world == 1:
+        if stats is not None:
+            stats.update(local_s=t1 - t0, gather_s=0.0, merge_s=0.0)
         return {k: np.asarray(mine[k]) for k in REACH_KEYS}
-    gathered = {k: all_gather_ragged(np.asarray(mine[k]), info, device) for k in ("pkg_off", "pkg_agents", "pkg_minhop", "vuln_aoff", "vuln_agents", "vuln_minhop")}
+    on_gpu = torch.device(device).type == "cuda"
+    gathered = {k: all_gather_ragged(np.asarray(mine[k]), info, device, keep_on_device=on_gpu and k in ("pkg_agents", "vuln_agents"))
+                for k in ("pkg_off", "pkg_agents", "pkg_minhop", "vuln_aoff", "vuln_agents", "vuln_minhop")}
+    t2 = mark()
     partials = []
     for r in range(info.world):
         p = {k: np.asarray(mine[k]) for k in ("pkg_ids", "vuln_ids", "vuln_poff", "vuln_pkgs")}
         p.update({k: gathered[k][r] for k in gathered})
         partials.append(p)
-    return merge_dependency_reach(partials, node_rank, device)
+    out = merge_dependency_reach(partials, node_rank, device)
+    t3 = mark()
+    if stats is not None:
+        stats.update(local_s=t1 - t0, gather_s=t2 - t1, merge_s=t3 - t2)
+    return out

@@ -54,13 +54,16 @@ def main() -> int:
     dg = DeviceGraph.adopt(tensors, n_nodes, n_entries, info.local_rank)
     local = lambda shard: dg.dependency_reach(shard, REACH_MASK, VULN_PKG_MASK)
     times = []
+    phases = []
     merged = None
     for _ in range(args.reps + 1):
         torch.cuda.synchronize(); abdist.barrier(info)
         t0 = time.perf_counter()
-        merged = abdist.dependency_reach_sharded(local, agents, node_rank, info, device)
+        st = {}
+        merged = abdist.dependency_reach_sharded(local, agents, node_rank, info, device, stats=st)
         torch.cuda.synchronize(); abdist.barrier(info)
         times.append(time.perf_counter() - t0)
+        phases.append(st)
     sharded_s = abdist.max_over_ranks(min(times[1:]), info, device)
     if info.rank == 0:
         t0 = time.perf_counter()
@@ -70,7 +73,9 @@ def main() -> int:
         line = {"what": "compute_dependency_reach, agent BFSs sharded across ranks + all-gather merge", "workload": args.workload, "n_gpus": info.world,
                 "agents": int(len(agents)), "nodes": n_nodes, "packages": int(len(whole["pkg_ids"])), "vulnerabilities": int(len(whole["vuln_ids"])),
                 "reach_pairs": int(len(whole["pkg_agents"])), "sharded_s": sharded_s, "unsplit_single_gpu_s": unsplit_s,
-                "agents_per_s": len(agents) / sharded_s, "equals_unsplit_device_answer": bool(same), "csr_broadcast": bstats}
+                "agents_per_s": len(agents) / sharded_s, "equals_unsplit_device_answer": bool(same), "csr_broadcast": bstats,
+                "rank0_phases_s": {k: round(v, 4) for k, v in phases[int(np.argmin(times[1:])) + 1].items()},
+                "vulnerability_pairs": int(len(whole["vuln_agents"]))}
         print(json.dumps(line), flush=True)
         if not same:
             return 1

@@ -129,3 +129,31 @@ def test_gloo_world2_broadcast_and_shard():
     assert "rank0-ok" in proc.stdout and "rank1-ok" in proc.stdout
     # dependency reach split over the two ranks (per-package union / minimum exchanged by all-gather) equals the unsplit answer
     assert "rank0-reach-ok" in proc.stdout and "rank1-reach-ok" in proc.stdout
+
+
+def test_walk_result_rebuilds_the_dense_histogram_from_packed_columns():
+    """The host result carries only the entity-type columns present in the batch (csrc/histpack.cuh); `hist` rebuilds the dense
+    table on first access and `hist_dict` (the reference's `affected_by_type`) reads the packed rows directly."""
+    from agent_bom_b200.engine import WalkResult
+    from agent_bom_b200.graph.schema import ENTITY_VALUES, N_ENTITY_TYPES
+
+    rng = np.random.default_rng(5)
+    dense = np.zeros((50, N_ENTITY_TYPES), np.uint32)
+    cols = np.array([0, 2, 3, 9, 17], dtype=np.int64)
+    dense[:, cols] = rng.integers(0, 400, size=(50, len(cols)))
+    dense[7] = 0
+    z = np.zeros(50, np.int32)
+    for dt in (np.uint16, np.uint32):
+        r = WalkResult(start=z.astype(np.int64), count=z, maxd=z, flags=z, nodes=np.zeros(0, np.int32), hist_packed=dense[:, cols].astype(dt), hist_cols=cols)
+        assert r._hist is None
+        assert r.hist_dict(3) == {ENTITY_VALUES[t]: int(c) for t, c in enumerate(dense[3]) if c}
+        assert r.hist_dict(7) == {} and r._hist is None
+        np.testing.assert_array_equal(r.hist, dense)
+        assert r.hist is r.hist and r.hist.dtype == np.uint32
+    empty = WalkResult(start=z.astype(np.int64), count=z, maxd=z, flags=z, nodes=np.zeros(0, np.int32), hist_packed=np.zeros((50, 0), np.uint16),
+                       hist_cols=np.zeros(0, np.int64))
+    assert not empty.hist.any() and empty.hist.shape == (50, N_ENTITY_TYPES)
+    plain = WalkResult(start=z.astype(np.int64), count=z, maxd=z, flags=z, nodes=np.zeros(0, np.int32))
+    assert plain.hist is None
+    plain.hist = dense
+    assert plain.hist is dense
