@@ -219,6 +219,15 @@ struct abb_graph {
     DevBuf d_histinfo, d_hist_packed;
     unsigned long long hist_info[2] = {0, 0};   // column mask, largest count of the walk just staged
     bool hist_info_valid = false;
+    // chunked host walks (walk_host_chunked): a large plain batch is walked in `chunks` consecutive source ranges; each range's node arena
+    // is DMA-copied to the host while the next range is walked (two device arenas, ping-pong)
+    int chunks = 8;                  // ABB_CHUNKS / option "chunks"; applies to batches of >= chunk_min queries (measured at L: 1 piece 43.9 ms, 4: 42.4, 8: 40.6)
+    int64_t chunk_min = 2 << 20;
+    DevBuf d_nodes_alt, ck_roots, ck_sig, ck_key, ck_key2, ck_idx, ck_order, ck_counts, ck_tmp, ck_qstart, ck_qcount, ck_qmaxd, ck_qflags, ck_qhist;
+    cudaEvent_t ev_chunk_walked = nullptr, ev_chunk_copied[2] = {nullptr, nullptr};
+    std::vector<int64_t> chunk_hint;   // nodes each chunk produced last time (same batch size / chunk count)
+    int64_t chunk_hint_nq = -1;
+    int last_host_chunks = 1;        // how many ranges the last host-buffer walk was split into (get_option "last_host_chunks")
     bool zero_copy = true;      // host-API walks write the node arena straight into pinned host memory when its size is known
     int64_t last_walk_queries = 0;
     bool last_walk_dedup = false;
@@ -257,6 +266,8 @@ static int graph_finish_init(abb_graph *g) {
     CUDA_TRY(cudaStreamCreateWithFlags(&g->copy_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&g->paths_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&g->ev_copy, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&g->ev_chunk_walked, cudaEventDisableTiming));
+    for (auto &e : g->ev_chunk_copied) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto &e : g->ev) CUDA_TRY(cudaEventCreate(&e));
     if (int rc = g->ctl.ensure(CTL_WORDS * sizeof(unsigned long long))) return rc;
     const int64_t n = g->v.n;
@@ -294,6 +305,8 @@ static int graph_finish_init(abb_graph *g) {
     if (const char *e = getenv("ABB_S1_MINB")) g->s1_minb = atoi(e) == 4 ? 4 : 5;
     if (const char *e = getenv("ABB_ZEROCOPY")) g->zero_copy = atoi(e) != 0;
     if (const char *e = getenv("ABB_HIST_PACK")) g->hist_pack = atoi(e) != 0;
+    if (const char *e = getenv("ABB_CHUNKS")) g->chunks = std::max(1, std::min(64, atoi(e)));
+    if (const char *e = getenv("ABB_CHUNK_MIN")) g->chunk_min = std::max<int64_t>(2, atoll(e));
     if (const char *e = getenv("ABB_ALIGN_DIRECT")) g->align_direct = atoi(e) != 0;
     if (!g->v.rank) {
         if (int rc = g->identity_rank.ensure(static_cast<size_t>(n + 1) * 4)) return rc;
@@ -402,6 +415,13 @@ extern "C" int abb_graph_set_option(abb_graph *g, const char *name, int64_t valu
         g->big_qcap = static_cast<int>(value);
     } else if (k == "zero_copy") g->zero_copy = value != 0;
     else if (k == "hist_pack") g->hist_pack = value != 0;
+    else if (k == "chunks") {
+        if (value < 1 || value > 64) return fail(ABB_ERR_ARG, "chunks must be in [1, 64]");
+        g->chunks = static_cast<int>(value);
+    } else if (k == "chunk_min") {
+        if (value < 2) return fail(ABB_ERR_ARG, "chunk_min must be >= 2");
+        g->chunk_min = value;
+    }
     else if (k == "big_limit") {
         if (value < 0) return fail(ABB_ERR_ARG, "big_limit must be >= 0");
         g->big_limit = value;
@@ -417,6 +437,9 @@ extern "C" int64_t abb_graph_get_option(const abb_graph *g, const char *name) {
     if (k == "big_qcap") return g->big_qcap;
     if (k == "zero_copy") return g->zero_copy;
     if (k == "hist_pack") return g->hist_pack;
+    if (k == "chunks") return g->chunks;
+    if (k == "chunk_min") return g->chunk_min;
+    if (k == "last_host_chunks") return g->last_host_chunks;
     if (k == "big_limit") return g->big_limit;
     return -1;
 }
@@ -429,8 +452,10 @@ extern "C" void abb_graph_free(abb_graph *g) {
     if (g->copy_stream) { cudaStreamSynchronize(g->copy_stream); cudaStreamDestroy(g->copy_stream); }
     if (g->paths_stream) { cudaStreamSynchronize(g->paths_stream); cudaStreamDestroy(g->paths_stream); }
     if (g->ev_copy) cudaEventDestroy(g->ev_copy);
+    if (g->ev_chunk_walked) cudaEventDestroy(g->ev_chunk_walked);
+    for (auto &e : g->ev_chunk_copied) if (e) cudaEventDestroy(e);
     for (auto &e : g->ev) if (e) cudaEventDestroy(e);
-    for (DevBuf *b : {&g->ctl, &g->ov1, &g->ov2, &g->ov3, &g->ov4, &g->b_gq, &g->b_gpar, &g->b_gdep, &g->g_bitmap, &g->g_queue, &g->g_par, &g->g_dep, &g->x_bitmap, &g->x_queue, &g->x_par, &g->x_dep, &g->dd_sig, &g->dd_ssig, &g->dd_q, &g->dd_sq, &g->dd_head, &g->dd_gid, &g->dd_hp, &g->dd_glen, &g->dd_goff, &g->dd_arena, &g->dd_memoff, &g->dd_memsrc, &g->dd_memstate, &g->dd_indiv, &g->dd_cnt, &g->dd_tmp, &g->dd_lkey, &g->dd_lkey2, &g->dd_lgid, &g->dd_order, &g->dd_gstart, &g->dd_gcount, &g->dd_gmaxd, &g->dd_gflags, &g->dd_ghist, &g->d_histinfo, &g->d_hist_packed, &g->identity_rank, &g->d_roots, &g->d_root_off,
+    for (DevBuf *b : {&g->ctl, &g->ov1, &g->ov2, &g->ov3, &g->ov4, &g->b_gq, &g->b_gpar, &g->b_gdep, &g->g_bitmap, &g->g_queue, &g->g_par, &g->g_dep, &g->x_bitmap, &g->x_queue, &g->x_par, &g->x_dep, &g->dd_sig, &g->dd_ssig, &g->dd_q, &g->dd_sq, &g->dd_head, &g->dd_gid, &g->dd_hp, &g->dd_glen, &g->dd_goff, &g->dd_arena, &g->dd_memoff, &g->dd_memsrc, &g->dd_memstate, &g->dd_indiv, &g->dd_cnt, &g->dd_tmp, &g->dd_lkey, &g->dd_lkey2, &g->dd_lgid, &g->dd_order, &g->dd_gstart, &g->dd_gcount, &g->dd_gmaxd, &g->dd_gflags, &g->dd_ghist, &g->d_histinfo, &g->d_hist_packed, &g->d_nodes_alt, &g->ck_roots, &g->ck_sig, &g->ck_key, &g->ck_key2, &g->ck_idx, &g->ck_order, &g->ck_counts, &g->ck_tmp, &g->ck_qstart, &g->ck_qcount, &g->ck_qmaxd, &g->ck_qflags, &g->ck_qhist, &g->identity_rank, &g->d_roots, &g->d_root_off,
                       &g->d_targets, &g->d_qstart, &g->d_qcount, &g->d_qmaxd, &g->d_qflags, &g->d_qestart, &g->d_qecount, &g->d_qhist, &g->d_nodes,
                       &g->d_parent, &g->d_depth, &g->d_edges, &g->d_totals, &g->p_findings, &g->p_counts, &g->p_off, &g->p_hops, &g->p_rels,
                       &g->p_ncred, &g->p_ntool, &g->p_scan_tmp, &g->srv_cred, &g->srv_tool, &g->pl_cnt, &g->pl_off, &g->pl_vs, &g->pl_rel, &g->pl_rows, &g->pl_roff, &g->pl_toff, &g->pl_need, &g->pl_ulist, &g->pl_nu, &g->pt_cnt, &g->pt_off, &g->pt_off_node, &g->pt_cnt_node, &g->pt_row, &g->pt_rel})
@@ -1064,6 +1089,189 @@ static int walk_collect(abb_graph *g, const abb_walk_spec *spec, const abb_walk_
     return ABB_OK;
 }
 
+// ------------------------------------------------------------------ chunked host walk
+// A large plain batch (one root per query, no parents / depths / edges) whose result size is known from the previous call is walked
+// in `chunks` pieces.  Piece k's node arena is copied to the host by the DMA engine (copy stream) while piece k+1 is walked, so the
+// PCIe transfer runs at DMA speed behind the traversal instead of at the speed of SM stores (zero-copy) or after it.  Sources are
+// assigned to pieces by frontier signature (signature mod chunks: a frontier group is never split, so nothing is walked or stored
+// twice); each piece is a complete walk of its own.  Per-query arrays stay on the device for the whole batch, are put back into
+// caller order by one scatter pass and cross once at the end.
+constexpr int ABB_RETRY_UNCHUNKED = 1 << 20;   // internal: the caller falls back to the one-piece path
+
+__global__ void add_base_kernel(int64_t *q_start, int64_t n, int64_t base) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) q_start[i] += base;
+}
+
+static bool chunked_applies(const abb_graph *g, const abb_walk_spec *spec, const int64_t *root_off, const int32_t *targets, int64_t nq) {
+    const uint32_t fl = spec->flags;
+    return g->chunks > 1 && nq >= g->chunk_min && nq >= 2 * g->chunks && !root_off && !targets &&
+           !(fl & (ABB_WALK_PARENTS | ABB_WALK_DEPTHS | ABB_WALK_EDGES | ABB_WALK_TARGET)) && g->hint_nq == nq && g->hint_last_nodes > 0;
+}
+
+static int walk_host_chunked(abb_graph *g, const abb_walk_spec *spec, const int32_t *roots, int64_t nq, abb_walk_result **out) {
+    NvtxRange nvtx_("walk_host_chunked");
+    cudaStream_t st = g->stream, cst = g->copy_stream;
+    const uint32_t fl = spec->flags;
+    const int K = g->chunks;
+    const size_t q = static_cast<size_t>(nq), q1 = q + 1;
+    const bool hist = (fl & ABB_WALK_HIST) != 0;
+    int rc = ABB_OK;
+#define ENS(buf, bytes) if (!rc) rc = g->buf.ensure(static_cast<size_t>(bytes))
+    ENS(d_roots, q1 * 4); ENS(d_qstart, q1 * 8); ENS(d_qcount, q1 * 4); ENS(d_qmaxd, q1 * 4); ENS(d_qflags, q1 * 4);
+    if (hist) ENS(d_qhist, q1 * ABB_N_ENTITY_TYPES * 4);
+    ENS(d_totals, 3 * sizeof(unsigned long long));
+    ENS(ck_roots, q1 * 4); ENS(ck_sig, q1 * 8); ENS(ck_key, q1 * 4); ENS(ck_key2, q1 * 4); ENS(ck_idx, q1 * 4); ENS(ck_order, q1 * 4); ENS(ck_counts, 64 * 8);
+    ENS(ck_qstart, q1 * 8); ENS(ck_qcount, q1 * 4); ENS(ck_qmaxd, q1 * 4); ENS(ck_qflags, q1 * 4);
+    if (rc) return rc;
+    const bool have_hint = g->chunk_hint_nq == nq && static_cast<int>(g->chunk_hint.size()) == K;
+    // host arena: last total plus slack (the one-piece zero-copy pass pads slices, so its total is an upper bound already)
+    const int64_t host_cap = g->hint_last_nodes + g->hint_last_nodes / (have_hint ? 64 : 8) + 4096ll * K;
+    std::unique_ptr<abb_walk_result, void (*)(abb_walk_result *)> r(new abb_walk_result(), abb_walk_result_free);
+    r->nq = nq; r->flags = fl;
+    if (!(r->q_start.alloc(q * 8) && r->q_count.alloc(q * 4) && r->q_maxd.alloc(q * 4) && r->q_flags.alloc(q * 4) && r->nodes.alloc(static_cast<size_t>(host_cap) * 4)))
+        return fail(ABB_ERR_NOMEM, "pinned host allocation failed");
+    auto drain = [&]() { cudaStreamSynchronize(st); cudaStreamSynchronize(cst); };
+    const unsigned qblocks = static_cast<unsigned>((nq + 255) / 256);
+    CUDA_TRY(cudaMemcpyAsync(g->d_roots.p, roots, q * 4, cudaMemcpyHostToDevice, st));
+    r->h2d = nq * 4;
+    CUDA_TRY(cudaEventRecord(g->ev[0], st));
+    // partition: chunk = frontier signature mod K when the walk de-duplicates (a frontier group is never split), contiguous ranges otherwise
+    abb_walk_io probe{}; probe.n_queries = nq;
+    const bool by_sig = dedup_applies(g, spec, &probe);
+    unsigned long long *sig = nullptr;
+    if (by_sig) {
+        sig = g->ck_sig.as<unsigned long long>();
+        dedup_sig_kernel<<<qblocks, 256, 0, st>>>(g->v, *spec, g->d_roots.as<int32_t>(), nq, sig, nullptr); g_launches++;
+    }
+    CUDA_TRY(cudaMemsetAsync(g->ck_counts.p, 0, 64 * 8, st));
+    chunk_key_kernel<<<qblocks, 256, 0, st>>>(sig, nq, K, g->ck_key.as<uint32_t>(), g->ck_idx.as<int32_t>(), g->ck_counts.as<unsigned long long>()); g_launches++;
+    {
+        size_t tmp = 0;
+        CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp, g->ck_key.as<uint32_t>(), g->ck_key2.as<uint32_t>(), g->ck_idx.as<int32_t>(), g->ck_order.as<int32_t>(), static_cast<int>(nq), 0, 6, st));
+        if ((rc = g->ck_tmp.ensure(tmp + 16))) { drain(); return rc; }
+        CUDA_TRY(cub::DeviceRadixSort::SortPairs(g->ck_tmp.p, tmp, g->ck_key.as<uint32_t>(), g->ck_key2.as<uint32_t>(), g->ck_idx.as<int32_t>(), g->ck_order.as<int32_t>(), static_cast<int>(nq), 0, 6, st));
+        g_launches++;
+    }
+    const int32_t *order = g->ck_order.as<int32_t>();      // order[i] = caller index of the i-th query in chunk order
+    gather_i32_kernel<<<qblocks, 256, 0, st>>>(g->d_roots.as<int32_t>(), order, g->ck_roots.as<int32_t>(), nq); g_launches++;
+    unsigned long long counts[64] = {0};
+    CUDA_TRY(cudaMemcpyAsync(counts, g->ck_counts.p, 64 * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    std::vector<int64_t> produced(static_cast<size_t>(K), 0);
+    int64_t node_base = 0, b0 = 0;
+    bool copied[2] = {false, false};
+    for (int k = 0; k < K; k++) {
+        const int64_t nk = static_cast<int64_t>(counts[k]);
+        const int set = k & 1;
+        if (!nk) continue;
+        DevBuf &arena = set ? g->d_nodes_alt : g->d_nodes;
+        int64_t cap = have_hint ? g->chunk_hint[static_cast<size_t>(k)] + g->chunk_hint[static_cast<size_t>(k)] / 64 + 4096
+                                : 2 * (g->hint_last_nodes / K) + 65536;
+        cap = std::max<int64_t>(cap, nk * 8);
+        unsigned long long totals[3] = {0, 0, 0};
+        bool done = false;
+        for (int attempt = 0; attempt < 3 && !done; attempt++) {
+            if (static_cast<size_t>(cap) * 4 > arena.cap && copied[set]) CUDA_TRY(cudaEventSynchronize(g->ev_chunk_copied[set]));   // about to reallocate it
+            if ((rc = arena.ensure(static_cast<size_t>(cap) * 4))) { drain(); return rc; }
+            if (copied[set]) CUDA_TRY(cudaStreamWaitEvent(st, g->ev_chunk_copied[set], 0));       // the arena's previous contents have left
+            abb_walk_io io{};
+            io.n_queries = nk; io.roots = g->ck_roots.as<int32_t>() + b0;
+            io.q_start = g->d_qstart.as<int64_t>() + b0; io.q_count = g->d_qcount.as<int32_t>() + b0; io.q_maxd = g->d_qmaxd.as<int32_t>() + b0;
+            io.q_flags = g->d_qflags.as<int32_t>() + b0;
+            io.q_hist = hist ? g->d_qhist.as<uint32_t>() + b0 * ABB_N_ENTITY_TYPES : nullptr;
+            io.nodes = arena.as<int32_t>(); io.node_cap = cap; io.totals = g->d_totals.as<unsigned long long>();
+            CUDA_TRY(cudaMemsetAsync(g->d_totals.as<unsigned long long>() + 2, 0, sizeof(unsigned long long), st));
+            if (int erc = enqueue_walk(g, spec, &io, st)) { drain(); return erc; }
+            CUDA_TRY(cudaMemcpyAsync(totals, g->d_totals.p, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            unsigned long long fatal = 0, fatal2 = 0;
+            CUDA_TRY(cudaMemcpy(&fatal, g->ctl.as<unsigned long long>() + CTL_FATAL, sizeof fatal, cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(&fatal2, g->ctl.as<unsigned long long>() + CTL_SET + CTL_FATAL, sizeof fatal2, cudaMemcpyDeviceToHost));
+            if (fatal || fatal2) { drain(); return fail(ABB_ERR_CAPACITY, "a traversal outgrew the global scratch tier (more than n_nodes+4096 queue entries)"); }
+            if (static_cast<int64_t>(totals[0]) <= cap) done = true; else cap = static_cast<int64_t>(totals[0]) + 4096;
+        }
+        if (!done) { drain(); return fail(ABB_ERR_CAPACITY, "walk arenas still too small after resize"); }
+        const int64_t tot = static_cast<int64_t>(totals[0]);
+        produced[static_cast<size_t>(k)] = tot;
+        if (node_base + tot > host_cap) {          // the host arena guess was too small: let the one-piece path redo the batch
+            drain();
+            g->chunk_hint_nq = -1;
+            return ABB_RETRY_UNCHUNKED;
+        }
+        if (node_base) { add_base_kernel<<<static_cast<unsigned>((nk + 255) / 256), 256, 0, st>>>(g->d_qstart.as<int64_t>() + b0, nk, node_base); g_launches++; }
+        CUDA_TRY(cudaEventRecord(g->ev_chunk_walked, st));
+        CUDA_TRY(cudaStreamWaitEvent(cst, g->ev_chunk_walked, 0));
+        if (tot) CUDA_TRY(cudaMemcpyAsync(r->nodes.as<int32_t>() + node_base, arena.p, static_cast<size_t>(tot) * 4, cudaMemcpyDeviceToHost, cst));
+        CUDA_TRY(cudaEventRecord(g->ev_chunk_copied[set], cst));
+        copied[set] = true;
+        node_base += tot;
+        b0 += nk;
+    }
+    if (b0 != nq) { drain(); return fail(ABB_ERR_CUDA, "chunk partition lost queries (%lld of %lld)", static_cast<long long>(b0), static_cast<long long>(nq)); }
+    CUDA_TRY(cudaEventRecord(g->ev[1], st));
+    g->walk_timed = true;
+    r->total_nodes = node_base;
+    r->d2h += node_base * 4;
+    // per-query results back into caller order, then to the host (the node copies of the last chunks are still in flight on the copy stream)
+    const unsigned sgrid = static_cast<unsigned>(g->sm_count) * 8;
+    scatter_rows_kernel<int64_t><<<sgrid, 256, 0, st>>>(g->d_qstart.as<int64_t>(), order, g->ck_qstart.as<int64_t>(), nq, 1);
+    scatter_rows_kernel<int32_t><<<sgrid, 256, 0, st>>>(g->d_qcount.as<int32_t>(), order, g->ck_qcount.as<int32_t>(), nq, 1);
+    scatter_rows_kernel<int32_t><<<sgrid, 256, 0, st>>>(g->d_qmaxd.as<int32_t>(), order, g->ck_qmaxd.as<int32_t>(), nq, 1);
+    scatter_rows_kernel<int32_t><<<sgrid, 256, 0, st>>>(g->d_qflags.as<int32_t>(), order, g->ck_qflags.as<int32_t>(), nq, 1);
+    g_launches += 4;
+    const bool scan_hist = hist && g->hist_pack && nq >= 1024;
+    if (scan_hist) {
+        if ((rc = g->d_histinfo.ensure(2 * sizeof(unsigned long long)))) { drain(); return rc; }
+        CUDA_TRY(cudaMemsetAsync(g->d_histinfo.p, 0, 2 * sizeof(unsigned long long), st));
+        hist_columns_kernel<<<sgrid, 256, 0, st>>>(g->d_qhist.as<uint32_t>(), nq * ABB_N_ENTITY_TYPES, g->d_histinfo.as<unsigned long long>());
+        g_launches++;
+        CUDA_TRY(cudaMemcpyAsync(g->hist_info, g->d_histinfo.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    cudaError_t e = cudaGetLastError();
+    auto d2h = [&](HostBlock &dst, const void *src, size_t bytes) {
+        r->d2h += static_cast<int64_t>(bytes);
+        if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(dst.p, src, bytes, cudaMemcpyDeviceToHost, st);
+    };
+    d2h(r->q_start, g->ck_qstart.p, q * 8); d2h(r->q_count, g->ck_qcount.p, q * 4); d2h(r->q_maxd, g->ck_qmaxd.p, q * 4); d2h(r->q_flags, g->ck_qflags.p, q * 4);
+    if (scan_hist) {
+        HistCols hc{};
+        r->hist_is_packed = true;
+        r->hist_mask = static_cast<uint32_t>(g->hist_info[0]);
+        for (int t = 0; t < ABB_N_ENTITY_TYPES; t++) if (r->hist_mask >> t & 1u) hc.col[hc.k++] = static_cast<uint8_t>(t);
+        r->hist_k = hc.k;
+        r->hist_width = g->hist_info[1] < 65536ull ? 2 : 4;
+        if (hc.k) {
+            const size_t pbytes = q * hc.k * r->hist_width;
+            if (!r->q_hist_packed.alloc(pbytes)) { drain(); return fail(ABB_ERR_NOMEM, "pinned host allocation failed"); }
+            if ((rc = g->d_hist_packed.ensure(pbytes))) { drain(); return rc; }
+            if (r->hist_width == 2) hist_pack_scatter_kernel<uint16_t><<<sgrid, 256, 0, st>>>(g->d_qhist.as<uint32_t>(), order, nq, hc, g->d_hist_packed.as<uint16_t>());
+            else hist_pack_scatter_kernel<uint32_t><<<sgrid, 256, 0, st>>>(g->d_qhist.as<uint32_t>(), order, nq, hc, g->d_hist_packed.as<uint32_t>());
+            g_launches++;
+            d2h(r->q_hist_packed, g->d_hist_packed.p, pbytes);
+        }
+    } else if (hist) {
+        if (!r->q_hist.alloc(q * ABB_N_ENTITY_TYPES * 4)) { drain(); return fail(ABB_ERR_NOMEM, "pinned host allocation failed"); }
+        if ((rc = g->ck_qhist.ensure(q1 * ABB_N_ENTITY_TYPES * 4))) { drain(); return rc; }
+        scatter_rows_kernel<uint32_t><<<sgrid, 256, 0, st>>>(g->d_qhist.as<uint32_t>(), order, g->ck_qhist.as<uint32_t>(), nq, ABB_N_ENTITY_TYPES);
+        g_launches++;
+        d2h(r->q_hist, g->ck_qhist.p, q * ABB_N_ENTITY_TYPES * 4);
+    }
+#undef ENS
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cst);
+    if (e != cudaSuccess) { drain(); return fail(ABB_ERR_CUDA, "chunked walk failed: %s", cudaGetErrorString(e)); }
+    g->hist_info_valid = false;
+    g->chunk_hint = produced; g->chunk_hint_nq = nq;
+    g->hint_nodes = std::max<int64_t>(g->hint_nodes, node_base);
+    g->hint_nq = nq; g->hint_last_nodes = node_base;
+    g->last_host_chunks = K;
+    *out = r.release();
+    return ABB_OK;
+}
+
 extern "C" int abb_walk_host(abb_graph *g, const abb_walk_spec *spec, const int32_t *roots, const int64_t *root_off, const int32_t *targets,
                              int64_t n_queries, abb_walk_result **out) {
     NvtxRange nvtx_("abb_walk_host");
@@ -1071,6 +1279,11 @@ extern "C" int abb_walk_host(abb_graph *g, const abb_walk_spec *spec, const int3
     if ((spec->flags & ABB_WALK_TARGET) && !targets) return fail(ABB_ERR_ARG, "TARGET needs targets");
     DeviceGuard dg(g->device);
     std::lock_guard<std::mutex> lk(g->mu);
+    if (chunked_applies(g, spec, root_off, targets, n_queries)) {
+        const int crc = walk_host_chunked(g, spec, roots, n_queries, out);
+        if (crc != ABB_RETRY_UNCHUNKED) return crc;
+    }
+    g->last_host_chunks = 1;
     abb_walk_io io{}; unsigned long long totals[3] = {0, 0, 0}; int64_t h2d = 0;
     HostBlock direct;
     if (int rc = walk_device_stage(g, spec, roots, root_off, targets, n_queries, &io, totals, &h2d, &direct)) { direct.release(); return rc; }
@@ -1459,9 +1672,14 @@ extern "C" int abb_exposure_host(abb_graph *g, const int32_t *findings, int64_t 
     abb_walk_io io{}; unsigned long long totals[3] = {0, 0, 0}; int64_t h2d = 0;
     HostBlock direct;
     abb_walk_result *wr = nullptr;
-    int rc = walk_device_stage(g, &spec, findings, nullptr, nullptr, n_findings, &io, totals, &h2d, &direct);
-    const auto t1 = now();
-    if (!rc) rc = walk_collect(g, &spec, io, totals, h2d, &wr, true, &direct);
+    int rc = chunked_applies(g, &spec, nullptr, nullptr, n_findings) ? walk_host_chunked(g, &spec, findings, n_findings, &wr) : ABB_RETRY_UNCHUNKED;
+    auto t1 = now();
+    if (rc == ABB_RETRY_UNCHUNKED) {
+        g->last_host_chunks = 1;
+        rc = walk_device_stage(g, &spec, findings, nullptr, nullptr, n_findings, &io, totals, &h2d, &direct);
+        t1 = now();
+        if (!rc) rc = walk_collect(g, &spec, io, totals, h2d, &wr, true, &direct);
+    }
     direct.release();
     const auto t2 = now();
     helper.join();

@@ -40,4 +40,52 @@ __global__ void hist_pack_kernel(const uint32_t *__restrict__ hist, int64_t nq, 
     }
 }
 
+// ---- chunked host walks (abb200.cu: walk_host_chunked): sources are partitioned into chunks by frontier signature (all members of a
+// frontier group land in one chunk), walked chunk by chunk in that order, and the per-query results are put back in caller order.
+
+// key[q] = chunk of query q; counts[c] += 1
+__global__ void chunk_key_kernel(const unsigned long long *__restrict__ sig, int64_t nq, int n_chunks, uint32_t *key, int32_t *idx, unsigned long long *counts) {
+    __shared__ unsigned int s_cnt[64];
+    if (threadIdx.x < 64) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t q = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (q < nq) {
+        const uint32_t c = sig ? static_cast<uint32_t>(sig[q] % static_cast<unsigned long long>(n_chunks)) : static_cast<uint32_t>(q * n_chunks / nq);
+        key[q] = c;
+        idx[q] = static_cast<int32_t>(q);
+        atomicAdd(&s_cnt[c], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < n_chunks && s_cnt[threadIdx.x]) atomicAdd(counts + threadIdx.x, static_cast<unsigned long long>(s_cnt[threadIdx.x]));
+}
+
+__global__ void gather_i32_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ idx, int32_t *__restrict__ dst, int64_t n) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = __ldg(src + __ldg(idx + i));
+}
+
+// dst[idx[i] * width + j] = src[i * width + j]
+template <class T>
+__global__ void scatter_rows_kernel(const T *__restrict__ src, const int32_t *__restrict__ idx, T *__restrict__ dst, int64_t n, int width) {
+    const int64_t n_elems = n * width;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < n_elems; e += stride) {
+        const int64_t i = e / width;
+        const int j = static_cast<int>(e - i * width);
+        dst[static_cast<int64_t>(__ldg(idx + i)) * width + j] = src[e];
+    }
+}
+
+// out[idx[q] * k + j] = hist[q * 24 + col[j]]
+template <class T>
+__global__ void hist_pack_scatter_kernel(const uint32_t *__restrict__ hist, const int32_t *__restrict__ idx, int64_t nq, HistCols hc, T *__restrict__ out) {
+    const int64_t n_out = nq * hc.k;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_out; i += stride) {
+        const int64_t q = i / hc.k;
+        const int j = static_cast<int>(i - q * hc.k);
+        out[static_cast<int64_t>(__ldg(idx + q)) * hc.k + j] = static_cast<T>(__ldg(hist + q * ABB_N_ENTITY_TYPES + hc.col[j]));
+    }
+}
+
 }  // namespace abb

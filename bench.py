@@ -608,7 +608,7 @@ def main() -> int:
             },
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_all), "d2h_bytes_per_step": int(d2h_all), "ms_per_step": 1000.0 * e2e_s_max / args.steps,
                     "first_call_ms": first_call_max, "python_zero_copy": {"value": total_findings * args.steps / e2e_py_max, "ms_per_step": 1000.0 * e2e_py_max / args.steps},
-                    "includes": "H2D of finding ids, frontier-signature sharding (N>1), walk + path kernels, D2H of per-source slices/histograms and of the factorised exposure-path rows "
+                    "includes": "H2D of finding ids, frontier-signature sharding (N>1), walk (in 8 signature-partitioned pieces above 2 M sources, each piece's arena DMA-copied behind the next piece's walk) + path kernels, D2H of per-source slices/packed histograms and of the factorised exposure-path rows "
                                 "(links + templates; the flat rows are expanded on the host on first access and are not part of this figure)"},
             "gpu_launches": int(launches),
             "walk_ms_per_step": walk_ms, "paths_ms_per_step": paths_ms, "sequential_ms_per_step": seq_ms,
