@@ -387,24 +387,7 @@ __device__ __forceinline__ bool expand_window_lean(const WalkArgs &A, Store &st,
         __syncwarp();
         return true;
     };
-#ifdef ABB_LEAN_XROW
-    // (experiment) the first chunk of the NEXT row is loaded while this row is probed
-    uint32_t s_nx = single ? my_s : __shfl_sync(FULL, my_s, 0), tot_nx = single ? my_d : __shfl_sync(FULL, my_d, 0);
-    int32_t v_nx = static_cast<uint32_t>(lane) < tot_nx ? __ldg(nbr + s_nx + lane) : EMPTY;
-#endif
     for (uint32_t j = 0; j < nrows; j++) {
-#ifdef ABB_LEAN_XROW
-        const uint32_t s = s_nx, tot = tot_nx;
-        int32_t v1 = v_nx;
-        if (j + 1 < nrows) {
-            s_nx = __shfl_sync(FULL, my_s, (j + 1) & 31); tot_nx = __shfl_sync(FULL, my_d, (j + 1) & 31);
-            v_nx = static_cast<uint32_t>(lane) < tot_nx ? __ldg(nbr + s_nx + lane) : EMPTY;
-        }
-        if (tot == 0) continue;
-        const int32_t *pl = nbr + s + lane;
-        const uint32_t rem0 = tot - min(tot, static_cast<uint32_t>(lane));
-        int32_t v2 = rem0 > 32u ? __ldg(pl + 32) : EMPTY;
-#else
         const uint32_t s = single ? my_s : __shfl_sync(FULL, my_s, j);
         const uint32_t tot = single ? my_d : __shfl_sync(FULL, my_d, j);
         if (tot == 0) continue;
@@ -413,7 +396,6 @@ __device__ __forceinline__ bool expand_window_lean(const WalkArgs &A, Store &st,
         // two chunks per step (two independent loads and probes per lane, one vote), the next two already in flight
         int32_t v1 = rem0 > 0u ? __ldg(pl) : EMPTY;
         int32_t v2 = rem0 > 32u ? __ldg(pl + 32) : EMPTY;
-#endif
         for (uint32_t c0 = 0; c0 < tot; c0 += 64, pl += 64) {
             const int32_t va = v1, vb = v2;
             v1 = (rem0 > c0 + 64u) ? __ldg(pl + 64) : EMPTY;
