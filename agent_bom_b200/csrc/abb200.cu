@@ -227,6 +227,9 @@ struct abb_graph {
     cudaEvent_t ev_chunk_walked = nullptr, ev_chunk_copied[2] = {nullptr, nullptr};
     std::vector<int64_t> chunk_hint;   // nodes each chunk produced last time (same batch size / chunk count)
     int64_t chunk_hint_nq = -1;
+    // size hint of the last PLAIN host walk (single roots, no parents / depths / edges), per spec: what the chunked path sizes its arenas from
+    abb_walk_spec plain_spec{};
+    int64_t plain_nq = -1, plain_nodes = 0;
     int last_host_chunks = 1;        // how many ranges the last host-buffer walk was split into (get_option "last_host_chunks")
     bool zero_copy = true;      // host-API walks write the node arena straight into pinned host memory when its size is known
     int64_t last_walk_queries = 0;
@@ -1018,7 +1021,13 @@ static int walk_device_stage(abb_graph *g, const abb_walk_spec *spec, const int3
         g->hint_nodes = std::max<int64_t>(g->hint_nodes, static_cast<int64_t>(totals[0]));
         g->hint_nq = nq; g->hint_last_nodes = static_cast<int64_t>(totals[0]);
         g->hint_edges = std::max<int64_t>(g->hint_edges, static_cast<int64_t>(totals[1]));
-        if (fits) return ABB_OK;
+        if (fits) {
+            if (!root_off && !(fl & (ABB_WALK_PARENTS | ABB_WALK_DEPTHS | ABB_WALK_EDGES | ABB_WALK_TARGET))) {
+                if (g->plain_nq != nq || memcmp(&g->plain_spec, spec, sizeof *spec) != 0) g->chunk_hint_nq = -1;
+                g->plain_spec = *spec; g->plain_nq = nq; g->plain_nodes = static_cast<int64_t>(totals[0]);
+            }
+            return ABB_OK;
+        }
         if (direct) { direct_nodes->release(); direct = false; }     // estimate too small: fall back to a device arena
         node_cap = std::max<int64_t>(node_cap, static_cast<int64_t>(totals[0]));
         edge_cap = std::max<int64_t>(edge_cap, static_cast<int64_t>(totals[1]));
@@ -1106,7 +1115,8 @@ __global__ void add_base_kernel(int64_t *q_start, int64_t n, int64_t base) {
 static bool chunked_applies(const abb_graph *g, const abb_walk_spec *spec, const int64_t *root_off, const int32_t *targets, int64_t nq) {
     const uint32_t fl = spec->flags;
     return g->chunks > 1 && nq >= g->chunk_min && nq >= 2 * g->chunks && !root_off && !targets &&
-           !(fl & (ABB_WALK_PARENTS | ABB_WALK_DEPTHS | ABB_WALK_EDGES | ABB_WALK_TARGET)) && g->hint_nq == nq && g->hint_last_nodes > 0;
+           !(fl & (ABB_WALK_PARENTS | ABB_WALK_DEPTHS | ABB_WALK_EDGES | ABB_WALK_TARGET)) && g->plain_nq == nq && g->plain_nodes > 0 &&
+           memcmp(&g->plain_spec, spec, sizeof *spec) == 0;
 }
 
 static int walk_host_chunked(abb_graph *g, const abb_walk_spec *spec, const int32_t *roots, int64_t nq, abb_walk_result **out) {
@@ -1126,7 +1136,7 @@ static int walk_host_chunked(abb_graph *g, const abb_walk_spec *spec, const int3
     if (rc) return rc;
     const bool have_hint = g->chunk_hint_nq == nq && static_cast<int>(g->chunk_hint.size()) == K;
     // host arena: last total plus slack (the one-piece zero-copy pass pads slices, so its total is an upper bound already)
-    const int64_t host_cap = g->hint_last_nodes + g->hint_last_nodes / (have_hint ? 64 : 8) + 4096ll * K;
+    const int64_t host_cap = g->plain_nodes + g->plain_nodes / (have_hint ? 64 : 8) + 4096ll * K;
     std::unique_ptr<abb_walk_result, void (*)(abb_walk_result *)> r(new abb_walk_result(), abb_walk_result_free);
     r->nq = nq; r->flags = fl;
     if (!(r->q_start.alloc(q * 8) && r->q_count.alloc(q * 4) && r->q_maxd.alloc(q * 4) && r->q_flags.alloc(q * 4) && r->nodes.alloc(static_cast<size_t>(host_cap) * 4)))
@@ -1167,7 +1177,7 @@ static int walk_host_chunked(abb_graph *g, const abb_walk_spec *spec, const int3
         if (!nk) continue;
         DevBuf &arena = set ? g->d_nodes_alt : g->d_nodes;
         int64_t cap = have_hint ? g->chunk_hint[static_cast<size_t>(k)] + g->chunk_hint[static_cast<size_t>(k)] / 64 + 4096
-                                : 2 * (g->hint_last_nodes / K) + 65536;
+                                : 2 * (g->plain_nodes / K) + 65536;
         cap = std::max<int64_t>(cap, nk * 8);
         unsigned long long totals[3] = {0, 0, 0};
         bool done = false;
@@ -1267,6 +1277,7 @@ static int walk_host_chunked(abb_graph *g, const abb_walk_spec *spec, const int3
     g->chunk_hint = produced; g->chunk_hint_nq = nq;
     g->hint_nodes = std::max<int64_t>(g->hint_nodes, node_base);
     g->hint_nq = nq; g->hint_last_nodes = node_base;
+    g->plain_spec = *spec; g->plain_nq = nq; g->plain_nodes = node_base;
     g->last_host_chunks = K;
     *out = r.release();
     return ABB_OK;
