@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define ABB_VERSION 100
+#define ABB_VERSION 110
 
 typedef enum abb_status {
     ABB_OK = 0,

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     missing = [s for s in sorted(declared) if not hasattr(lib, s)]
     assert not missing, f"libabb200.so lacks {missing}"
     assert declared == set(_lib.EXPORTS), f"binding table out of sync: {declared ^ set(_lib.EXPORTS)}"
-    assert lib.abb_version() == 100
+    assert lib.abb_version() == 110
 
 
 def test_no_cpu_fallback_without_device():
