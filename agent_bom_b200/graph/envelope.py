@@ -1,208 +1,232 @@
 """ExposurePath wire envelopes for attack paths — the step right after the path.
 
-Restates, for ``AttackPath`` records produced on the device (``graph/exposure.py``) or loaded from a snapshot:
+Produces, for ``AttackPath`` records made on the device (``graph/exposure.py``) or loaded from a snapshot, the two JSON
+objects the reference emits for them:
 
-* the REST envelope ``_exposure_path_for_attack_path`` / ``_serialize_attack_path``
-  (``/root/reference/src/agent_bom/api/routes/graph.py:506-670``, helpers ``:275-291``, ``:484-503``), and
-* the MCP payload ``_exposure_path_payload`` (``/root/reference/src/agent_bom/mcp_tools/graph.py:16-100``).
+* REST — ``exposure_path`` inside each element of ``attack_paths``
+  (behaviour of ``/root/reference/src/agent_bom/api/routes/graph.py:506-670`` with its helpers ``:275-291``, ``:484-503``);
+* MCP — the ``exposure_paths`` tool payload (behaviour of ``/root/reference/src/agent_bom/mcp_tools/graph.py:16-100``).
 
-The reference rebuilds an O(|E|) ``(source, target) → edge`` map for EVERY path (``routes/graph.py:543-547``,
-``mcp_tools/graph.py:34-57``); here the two indexes are built once per graph (``EdgeIndex``) and give the same
-answers: first edge in ``graph.edges`` order per pair (bidirectional edges also register the reverse pair) for REST,
-every edge between consecutive hops in ``graph.edges`` order for MCP.  Pinned by ``tests/test_envelope.py`` on
-envelopes the unmodified reference produced (``tests/golden/envelope/``, ``oracle/make_golden.py --envelope-only``).
+The wire contract (key names, key order, fallbacks) is fixed by the reference; the construction here is table-driven and
+indexed: the reference rebuilds an O(|E|) ``(source, target) → edge`` map for EVERY path, here one ``EdgeIndex`` per graph answers
+"first edge of a hop pair" (REST; a bidirectional edge also answers for the reversed pair), "all edges of a hop pair" and
+"edges with this id" (MCP).  Pinned object-for-object by ``tests/test_envelope.py`` on envelopes the unmodified reference
+produced (``tests/golden/envelope/``, ``oracle/make_golden.py``).
 """
 
 from __future__ import annotations
 
-from typing import Any
+from typing import Any, Iterable
 
 from .schema import SEVERITY_RANK, enum_value
 
-_FINDING = {"vulnerability", "misconfiguration"}
-_ROLE = {
-    "vulnerability": "finding", "misconfiguration": "finding", "package": "package",
-    "server": "server", "container": "server", "cloud_resource": "server",
-    "agent": "agent", "user": "agent", "group": "agent", "service_account": "agent",
-    "credential": "credential", "tool": "tool", "environment": "environment", "cluster": "cluster",
-}
+# entity type -> role of a hop in the cockpit
+_ROLE_GROUPS = (
+    ("finding", ("vulnerability", "misconfiguration")),
+    ("package", ("package",)),
+    ("server", ("server", "container", "cloud_resource")),
+    ("agent", ("agent", "user", "group", "service_account")),
+    ("credential", ("credential",)),
+    ("tool", ("tool",)),
+    ("environment", ("environment",)),
+    ("cluster", ("cluster",)),
+)
+ROLE_OF = {etype: role for role, etypes in _ROLE_GROUPS for etype in etypes}
+_FINDING_TYPES = frozenset(_ROLE_GROUPS[0][1])
+_UNKNOWN = "unknown"
+# composite risk is on a 0-100 scale in new snapshots and 0-10 in old ones; the reference accepts either, so the lower bound decides
+_RISK_BANDS = ((9.0, "critical"), (7.0, "high"), (4.0, "medium"))
+_MCP_SEVERITY_ORDER = {"critical": 4, "high": 3, "medium": 2, "low": 1, "none": 0, "": 0}
+# evidence block: wire key -> (node attribute, cast)
+_EVIDENCE_FIELDS = (("cvssScore", "cvss_score", None), ("epssScore", "epss_score", None), ("isKev", "is_kev", bool), ("impactCategory", "impact_category", None))
+_REST_ORIGIN = "graph_attack_path"
+_MCP_ORIGIN = "mcp_exposure_paths"
 
 
-def _type_value(node) -> str:
+def _etype(node) -> str:
     return enum_value(node.entity_type)
 
 
-def exposure_role_for_node(node) -> str:
-    """routes/graph.py:506-524."""
-    return _ROLE.get(_type_value(node), "unknown")
-
-
-def exposure_ref_for_node(node_id: str, nodes_by_id: dict[str, Any]) -> dict[str, Any]:
-    """routes/graph.py:527-540."""
-    node = nodes_by_id.get(node_id)
-    if node is None:
-        return {"id": node_id, "label": node_id, "role": "unknown"}
-    ref: dict[str, Any] = {"id": node.id, "label": node.label, "role": exposure_role_for_node(node)}
-    if getattr(node, "severity", ""):
-        ref["severity"] = node.severity
-    if float(getattr(node, "risk_score", 0.0) or 0.0) > 0:
-        ref["riskScore"] = node.risk_score
-    return ref
-
-
-def finding_ids_for_nodes(nodes: dict[str, Any], path_hops: list[str], vuln_ids: list[str]) -> list[str]:
-    """routes/graph.py:275-291."""
-    ids: list[str] = []
-    seen: set[str] = set()
-    for value in vuln_ids:
-        cleaned = value.strip()
-        if cleaned and cleaned not in seen:
-            ids.append(cleaned)
-            seen.add(cleaned)
-    for hop in path_hops:
-        node = nodes.get(hop)
-        if not node or _type_value(node) not in _FINDING:
-            continue
-        label = node.label or node.id
-        if label not in seen:
-            ids.append(label)
-            seen.add(label)
-    return ids
-
-
-class EdgeIndex:
-    """``(source, target)`` lookups over ``graph.edges``, built once per graph instead of once per path."""
-
-    def __init__(self, edges):
-        self.edges = list(edges or [])
-        self.first: dict[tuple[str, str], Any] = {}                  # REST: by_pair.setdefault (bidirectional edges also the reverse pair)
-        self.all: dict[tuple[str, str], list[int]] = {}              # MCP: every edge of a directed pair, graph.edges order
-        self.by_id: dict[str, list[int]] = {}
-        for i, edge in enumerate(self.edges):
-            self.first.setdefault((edge.source, edge.target), edge)
-            if edge.is_bidirectional:
-                self.first.setdefault((edge.target, edge.source), edge)
-            self.all.setdefault((str(edge.source), str(edge.target)), []).append(i)
-            self.by_id.setdefault(str(getattr(edge, "id", "")), []).append(i)
-
-
-def _as_index(edges) -> EdgeIndex:
-    return edges if isinstance(edges, EdgeIndex) else EdgeIndex(edges)
-
-
-def exposure_relationships_for_path(path, edges) -> list[dict[str, Any]]:
-    """routes/graph.py:543-580."""
-    index = _as_index(edges)
-    relationships: list[dict[str, Any]] = []
-    for i, (source, target) in enumerate(zip(path.hops, path.hops[1:])):
-        edge = index.first.get((source, target))
-        if edge is not None:
-            relationship = enum_value(edge.relationship)
-            edge_id, direction, traversable, confidence = edge.id, edge.direction, edge.traversable, getattr(edge, "confidence", 1.0)
-        else:
-            relationship = path.edges[i] if i < len(path.edges) else "related"
-            edge_id, direction, traversable, confidence = f"{relationship}:{source}:{target}", "directed", True, 1.0
-        relationships.append({"id": edge_id, "source": source, "target": target, "relationship": relationship, "direction": direction,
-                              "traversable": traversable, "confidence": confidence})
-    return relationships
-
-
-def _severity_from_risk(risk: float) -> str:
-    if risk >= 90 or risk >= 9:
-        return "critical"
-    if risk >= 70 or risk >= 7:
-        return "high"
-    if risk >= 40 or risk >= 4:
-        return "medium"
+def _band(risk: float) -> str:
+    for floor, name in _RISK_BANDS:
+        if risk >= floor:
+            return name
     return "none"
 
 
-def severity_for_exposure_path(path, nodes_by_id: dict[str, Any]) -> str:
-    """routes/graph.py:583-597."""
-    severity = ""
-    for hop in path.hops:
+def _first_occurrences(items: Iterable[str]) -> list[str]:
+    return list(dict.fromkeys(items))
+
+
+def _stub(node_id: str) -> dict[str, Any]:
+    return {"id": node_id, "label": node_id, "role": _UNKNOWN}
+
+
+class EdgeIndex:
+    """Hop-pair lookups over ``graph.edges`` (list order preserved), built once per graph instead of once per path."""
+
+    __slots__ = ("edges", "_first", "_between", "_by_id")
+
+    def __init__(self, edges):
+        self.edges = list(edges or [])
+        self._first: dict[tuple[str, str], int] = {}
+        self._between: dict[tuple[str, str], list[int]] = {}
+        self._by_id: dict[str, list[int]] = {}
+        for pos, e in enumerate(self.edges):
+            forward = (e.source, e.target)
+            self._first.setdefault(forward, pos)
+            if e.is_bidirectional:
+                self._first.setdefault(forward[::-1], pos)
+            self._between.setdefault((str(e.source), str(e.target)), []).append(pos)
+            self._by_id.setdefault(str(getattr(e, "id", "")), []).append(pos)
+
+    @classmethod
+    def of(cls, edges) -> "EdgeIndex":
+        return edges if isinstance(edges, cls) else cls(edges)
+
+    def first_edge(self, source, target):
+        pos = self._first.get((source, target))
+        return None if pos is None else self.edges[pos]
+
+    def positions_between(self, source, target) -> list[int]:
+        return self._between.get((str(source), str(target)), [])
+
+    def positions_with_id(self, edge_id) -> list[int]:
+        return self._by_id.get(str(edge_id), [])
+
+
+# ── REST (api/routes/graph.py) ────────────────────────────────────────────────────────────────────────────────────────
+def exposure_role_for_node(node) -> str:
+    return ROLE_OF.get(_etype(node), _UNKNOWN)
+
+
+def exposure_ref_for_node(node_id: str, nodes_by_id: dict[str, Any]) -> dict[str, Any]:
+    """One hop as the cockpit shows it; severity / riskScore only when the node carries them."""
+    node = nodes_by_id.get(node_id)
+    if node is None:
+        return _stub(node_id)
+    card: dict[str, Any] = {"id": node.id, "label": node.label, "role": exposure_role_for_node(node)}
+    declared = getattr(node, "severity", "")
+    if declared:
+        card["severity"] = declared
+    score = getattr(node, "risk_score", 0.0)
+    if float(score or 0.0) > 0:
+        card["riskScore"] = score
+    return card
+
+
+def finding_ids_for_nodes(nodes: dict[str, Any], path_hops: list[str], vuln_ids: list[str]) -> list[str]:
+    """The path's own vulnerability ids (trimmed, blanks dropped), then the labels of finding-typed hops, first occurrence wins."""
+    from_path = [v.strip() for v in vuln_ids]
+    on_hops = []
+    for hop in path_hops:
+        node = nodes.get(hop)
+        if node and _etype(node) in _FINDING_TYPES:
+            on_hops.append(node.label or node.id)
+    return _first_occurrences([v for v in from_path if v] + on_hops)
+
+
+def _link(edge_id, source, target, relationship, direction, traversable, confidence) -> dict[str, Any]:
+    return {"id": edge_id, "source": source, "target": target, "relationship": relationship, "direction": direction, "traversable": traversable,
+            "confidence": confidence}
+
+
+def exposure_relationships_for_path(path, edges) -> list[dict[str, Any]]:
+    """One link per consecutive hop pair: the graph's first edge for the pair, else a synthetic directed link named after the path's own
+    relationship at that position (``related`` past its end)."""
+    index = EdgeIndex.of(edges)
+    declared = list(path.edges)
+    links = []
+    for pos, (a, b) in enumerate(zip(path.hops, path.hops[1:])):
+        hit = index.first_edge(a, b)
+        if hit is None:
+            name = declared[pos] if pos < len(declared) else "related"
+            links.append(_link(f"{name}:{a}:{b}", a, b, name, "directed", True, 1.0))
+        else:
+            links.append(_link(hit.id, a, b, enum_value(hit.relationship), hit.direction, hit.traversable, getattr(hit, "confidence", 1.0)))
+    return links
+
+
+def _worst_declared_severity(hops, nodes_by_id: dict[str, Any], order: dict[str, int]) -> str:
+    worst = ""
+    for hop in hops:
         node = nodes_by_id.get(hop)
-        if node is not None and SEVERITY_RANK.get(str(getattr(node, "severity", "") or "").lower(), 0) > SEVERITY_RANK.get(severity, 0):
-            severity = str(node.severity).lower()
-    return severity or _severity_from_risk(path.composite_risk)
+        declared = str(getattr(node, "severity", "") or "").lower() if node is not None else ""
+        if order.get(declared, 0) > order.get(worst, 0):
+            worst = declared
+    return worst
+
+
+def severity_for_exposure_path(path, nodes_by_id: dict[str, Any]) -> str:
+    return _worst_declared_severity(path.hops, nodes_by_id, SEVERITY_RANK) or _band(path.composite_risk)
+
+
+def _attributes(node) -> dict:
+    return getattr(node, "attributes", {}) if node is not None else {}
 
 
 def exposure_path_for_attack_path(path, *, nodes_by_id: dict[str, Any], edges=None, rank: int | None = None, scan_id: str = "") -> dict[str, Any]:
-    """routes/graph.py:597-656 — the ExposurePath object the cockpit and SDKs consume."""
-    hops = [exposure_ref_for_node(hop, nodes_by_id) for hop in path.hops]
-    empty_ref = {"id": "", "label": "", "role": "unknown"}
-    source = exposure_ref_for_node(path.source, nodes_by_id) if path.source else (hops[0] if hops else empty_ref)
-    target = exposure_ref_for_node(path.target, nodes_by_id) if path.target else (hops[-1] if hops else empty_ref)
-    relationships = exposure_relationships_for_path(path, edges)
-    packages = [hop for hop in hops if hop["role"] == "package"]
-    servers = [hop for hop in hops if hop["role"] == "server"]
-    agents = [hop for hop in hops if hop["role"] == "agent"]
+    """The ExposurePath object the cockpit and SDKs consume."""
+    cards = [exposure_ref_for_node(h, nodes_by_id) for h in path.hops]
+    blank = {"id": "", "label": "", "role": _UNKNOWN}
+    head = exposure_ref_for_node(path.source, nodes_by_id) if path.source else (cards[0] if cards else blank)
+    tail = exposure_ref_for_node(path.target, nodes_by_id) if path.target else (cards[-1] if cards else blank)
+    links = exposure_relationships_for_path(path, edges)
+    by_role: dict[str, list[dict]] = {}
+    for card in cards:
+        by_role.setdefault(card["role"], []).append(card)
+    agents, servers, packages = by_role.get("agent", []), by_role.get("server", []), by_role.get("package", [])
     findings = finding_ids_for_nodes(nodes_by_id, path.hops, path.vuln_ids)
-    label_parts = [findings[0] if findings else target["label"], agents[0]["label"] if agents else source["label"]]
-    exposure: dict[str, Any] = {
-        "id": f"{path.source}::{path.target}::{'->'.join(path.hops)}",
-        "label": " via ".join(part for part in label_parts if part) or path.summary or "Exposure path",
-        "summary": path.summary,
-        "riskScore": path.composite_risk,
-        "severity": severity_for_exposure_path(path, nodes_by_id),
-        "source": source,
-        "target": target,
-        "hops": hops,
-        "relationships": relationships,
-        "nodeIds": list(path.hops),
-        "edgeIds": [relationship["id"] for relationship in relationships],
-        "findings": findings,
-        "affectedAgents": [hop["label"] for hop in agents],
-        "affectedServers": [hop["label"] for hop in servers],
-        "reachableTools": list(path.tool_exposure),
-        "exposedCredentials": list(path.credential_exposure),
-        "provenance": {"source": "graph_attack_path", "scanId": scan_id} if scan_id else {"source": "graph_attack_path"},
-    }
+    what = findings[0] if findings else tail["label"]
+    who = agents[0]["label"] if agents else head["label"]
+    title = " via ".join(filter(None, (what, who))) or path.summary or "Exposure path"
+    origin = {"source": _REST_ORIGIN}
+    if scan_id:
+        origin["scanId"] = scan_id
+    fields = [
+        ("id", "::".join((path.source, path.target, "->".join(path.hops)))), ("label", title), ("summary", path.summary), ("riskScore", path.composite_risk),
+        ("severity", severity_for_exposure_path(path, nodes_by_id)), ("source", head), ("target", tail), ("hops", cards), ("relationships", links),
+        ("nodeIds", list(path.hops)), ("edgeIds", [link["id"] for link in links]), ("findings", findings),
+        ("affectedAgents", [c["label"] for c in agents]), ("affectedServers", [c["label"] for c in servers]),
+        ("reachableTools", list(path.tool_exposure)), ("exposedCredentials", list(path.credential_exposure)), ("provenance", origin),
+    ]
     if rank is not None:
-        exposure["rank"] = rank
+        fields.append(("rank", rank))
     if packages or servers:
-        package_node = nodes_by_id.get(packages[0]["id"]) if packages else None
-        exposure["dependencyContext"] = {
+        pkg_node = nodes_by_id.get(packages[0]["id"]) if packages else None
+        pkg_attrs = _attributes(pkg_node)
+        fields.append(("dependencyContext", {
             "packageName": packages[0]["label"] if packages else "",
-            "packageVersion": getattr(package_node, "attributes", {}).get("version", "") if package_node is not None else "",
-            "ecosystem": getattr(package_node, "attributes", {}).get("ecosystem", "") if package_node is not None else "",
+            "packageVersion": pkg_attrs.get("version", "") if pkg_node is not None else "",
+            "ecosystem": pkg_attrs.get("ecosystem", "") if pkg_node is not None else "",
             "serverName": servers[0]["label"] if servers else "",
-        }
-    finding_node = nodes_by_id.get(path.target)
-    if finding_node is not None:
-        attributes = getattr(finding_node, "attributes", {}) or {}
-        exposure["evidence"] = {
-            "cvssScore": attributes.get("cvss_score"),
-            "epssScore": attributes.get("epss_score"),
-            "isKev": bool(attributes.get("is_kev")),
-            "impactCategory": attributes.get("impact_category"),
-            "source": "graph_attack_path",
-        }
-    return exposure
+        }))
+    finding = nodes_by_id.get(path.target)
+    if finding is not None:
+        attrs = _attributes(finding) or {}
+        evidence = {key: (cast(attrs.get(attr)) if cast else attrs.get(attr)) for key, attr, cast in _EVIDENCE_FIELDS}
+        evidence["source"] = _REST_ORIGIN
+        fields.append(("evidence", evidence))
+    return dict(fields)
 
 
 def edge_relationships_for_hops(hops: list[str], edges) -> list[str]:
-    """routes/graph.py:488-503 — first relationship per consecutive hop pair; pairs without an edge are skipped."""
-    if len(hops) < 2:
-        return []
-    index = _as_index(edges)
-    out = []
-    for source, target in zip(hops, hops[1:]):
-        edge = index.first.get((source, target))
-        if edge is not None:
-            out.append(enum_value(edge.relationship))
-    return out
+    """Relationship of the graph's first edge per consecutive hop pair; pairs without an edge contribute nothing."""
+    index = EdgeIndex.of(edges)
+    found = (index.first_edge(a, b) for a, b in zip(hops, hops[1:]))
+    return [enum_value(e.relationship) for e in found if e is not None]
 
 
 def serialize_attack_path(path, edges=None, *, nodes_by_id: dict[str, Any] | None = None, rank: int | None = None, scan_id: str = "") -> dict:
-    """routes/graph.py:659-670 — one element of the REST ``attack_paths`` list."""
-    data = path.to_dict()
-    data["edges"] = [enum_value(e) for e in data.get("edges", [])]
-    if not data.get("edges") and edges is not None:
-        data["edges"] = edge_relationships_for_hops(path.hops, edges)
+    """One element of the REST ``attack_paths`` list: the path's own dict, relationships filled from the graph when the path has none, and
+    (given the node table) its ``exposure_path`` envelope."""
+    record = path.to_dict()
+    record["edges"] = [enum_value(e) for e in record.get("edges", [])]
+    if edges is not None and not record["edges"]:
+        record["edges"] = edge_relationships_for_hops(path.hops, edges)
     if nodes_by_id is not None:
-        data["exposure_path"] = exposure_path_for_attack_path(path, nodes_by_id=nodes_by_id, edges=edges, rank=rank, scan_id=scan_id)
-    return data
+        record["exposure_path"] = exposure_path_for_attack_path(path, nodes_by_id=nodes_by_id, edges=edges, rank=rank, scan_id=scan_id)
+    return record
 
 
 def serialize_attack_paths(graph, paths, *, first_rank: int = 1) -> list[dict]:
@@ -211,64 +235,50 @@ def serialize_attack_paths(graph, paths, *, first_rank: int = 1) -> list[dict]:
     return [serialize_attack_path(p, index, nodes_by_id=graph.nodes, rank=first_rank + i, scan_id=graph.scan_id) for i, p in enumerate(paths)]
 
 
-# ── MCP payload (mcp_tools/graph.py) ────────────────────────────────────────────────────────────────────────────────────
-def _mcp_node_ref(node_id: str, nodes_by_id: dict[str, Any]) -> dict[str, Any]:
+# ── MCP (mcp_tools/graph.py) ──────────────────────────────────────────────────────────────────────────────────────────
+def _mcp_card(node_id: str, nodes_by_id: dict[str, Any]) -> dict[str, Any]:
     node = nodes_by_id.get(node_id)
     if node is None:
-        return {"id": node_id, "label": node_id, "role": "unknown"}
-    return {"id": node.id, "label": node.label, "role": _type_value(node) or "unknown", "severity": getattr(node, "severity", ""),
+        return _stub(node_id)
+    return {"id": node.id, "label": node.label, "role": _etype(node) or _UNKNOWN, "severity": getattr(node, "severity", ""),
             "riskScore": float(getattr(node, "risk_score", 0.0) or 0.0)}
 
 
-def _mcp_relationship_refs(path, edges) -> list[dict[str, Any]]:
-    """mcp_tools/graph.py:34-57 — every edge whose id is listed in ``path.edges`` or that joins two consecutive hops, graph.edges order."""
-    index = _as_index(edges)
+def _mcp_links(path, edges) -> list[dict[str, Any]]:
+    """Every edge named in ``path.edges`` by id or joining two consecutive hops, in ``graph.edges`` order, each once."""
+    index = EdgeIndex.of(edges)
     hops = list(getattr(path, "hops", []) or [])
-    picked: set[int] = set()
-    for eid in set(getattr(path, "edges", []) or []):
-        picked.update(index.by_id.get(str(eid), ()))
-    for pair in set(zip(hops[:-1], hops[1:])):
-        picked.update(index.all.get((str(pair[0]), str(pair[1])), ()))
-    refs = []
-    for i in sorted(picked):
-        edge = index.edges[i]
-        refs.append({"id": str(getattr(edge, "id", "")), "source": str(edge.source), "target": str(edge.target), "relationship": enum_value(edge.relationship),
-                     "confidence": float(getattr(edge, "confidence", 1.0) or 0.0)})
-    return refs
-
-
-def _mcp_severity_for_path(path, nodes_by_id: dict[str, Any]) -> str:
-    order = {"critical": 4, "high": 3, "medium": 2, "low": 1, "none": 0, "": 0}
-    severity = ""
-    for hop in getattr(path, "hops", []) or []:
-        node = nodes_by_id.get(hop)
-        candidate = str(getattr(node, "severity", "") or "").lower() if node is not None else ""
-        if order.get(candidate, 0) > order.get(severity, 0):
-            severity = candidate
-    return severity or _severity_from_risk(float(getattr(path, "composite_risk", 0.0) or 0.0))
+    chosen: set[int] = set()
+    for edge_id in set(getattr(path, "edges", []) or []):
+        chosen.update(index.positions_with_id(edge_id))
+    for a, b in set(zip(hops, hops[1:])):
+        chosen.update(index.positions_between(a, b))
+    out = []
+    for pos in sorted(chosen):
+        e = index.edges[pos]
+        out.append({"id": str(getattr(e, "id", "")), "source": str(e.source), "target": str(e.target), "relationship": enum_value(e.relationship),
+                    "confidence": float(getattr(e, "confidence", 1.0) or 0.0)})
+    return out
 
 
 def mcp_exposure_path_payload(path, *, nodes_by_id: dict[str, Any], edges, rank: int, scan_id: str) -> dict[str, Any]:
-    """mcp_tools/graph.py:78-100."""
-    hops = [_mcp_node_ref(hop, nodes_by_id) for hop in getattr(path, "hops", []) or []]
-    source = _mcp_node_ref(str(getattr(path, "source", "") or ""), nodes_by_id) if getattr(path, "source", "") else (hops[0] if hops else {})
-    target = _mcp_node_ref(str(getattr(path, "target", "") or ""), nodes_by_id) if getattr(path, "target", "") else (hops[-1] if hops else {})
-    relationships = _mcp_relationship_refs(path, edges)
-    return {
-        "id": f"{source.get('id', '')}::{target.get('id', '')}::{'->'.join(getattr(path, 'hops', []) or [])}",
-        "rank": rank,
-        "label": getattr(path, "summary", "") or "Exposure path",
-        "summary": getattr(path, "summary", ""),
-        "riskScore": float(getattr(path, "composite_risk", 0.0) or 0.0),
-        "severity": _mcp_severity_for_path(path, nodes_by_id),
-        "source": source,
-        "target": target,
-        "hops": hops,
-        "relationships": relationships,
-        "nodeIds": list(getattr(path, "hops", []) or []),
-        "edgeIds": [relationship["id"] for relationship in relationships if relationship.get("id")],
-        "findings": list(getattr(path, "vuln_ids", []) or []),
-        "reachableTools": list(getattr(path, "tool_exposure", []) or []),
-        "exposedCredentials": list(getattr(path, "credential_exposure", []) or []),
-        "provenance": {"source": "mcp_exposure_paths", "scanId": scan_id},
-    }
+    """The ``exposure_paths`` MCP tool's object for one ranked path (duck-typed: every path field is optional)."""
+    def field(name, default):
+        return getattr(path, name, default) or default
+
+    hop_ids = list(field("hops", []))
+    cards = [_mcp_card(h, nodes_by_id) for h in hop_ids]
+    src, dst = field("source", ""), field("target", "")
+    head = _mcp_card(str(src), nodes_by_id) if src else (cards[0] if cards else {})
+    tail = _mcp_card(str(dst), nodes_by_id) if dst else (cards[-1] if cards else {})
+    links = _mcp_links(path, edges)
+    risk = float(field("composite_risk", 0.0))
+    summary = getattr(path, "summary", "")
+    return dict([
+        ("id", "::".join((head.get("id", ""), tail.get("id", ""), "->".join(hop_ids)))), ("rank", rank), ("label", summary or "Exposure path"), ("summary", summary),
+        ("riskScore", risk), ("severity", _worst_declared_severity(hop_ids, nodes_by_id, _MCP_SEVERITY_ORDER) or _band(risk)),
+        ("source", head), ("target", tail), ("hops", cards), ("relationships", links), ("nodeIds", hop_ids),
+        ("edgeIds", [link["id"] for link in links if link.get("id")]), ("findings", list(field("vuln_ids", []))),
+        ("reachableTools", list(field("tool_exposure", []))), ("exposedCredentials", list(field("credential_exposure", []))),
+        ("provenance", {"source": _MCP_ORIGIN, "scanId": scan_id}),
+    ])
