@@ -46,3 +46,12 @@ def test_reference_arm_other_ranks_exit_silently():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2")
     proc = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--workload", "S", "--gpus", "2"], capture_output=True, text=True, timeout=120, env=env)
     assert proc.returncode == 0 and proc.stdout.strip() == ""
+
+
+def test_only_the_json_line_reaches_stdout():
+    """Library chatter written to file descriptor 1 (NCCL's version banner at N > 1) or printed must not pollute the one-line contract."""
+    code = "import os, bench; bench.claim_stdout(); os.write(1, b'NCCL version 2.28.9+cuda12.9\\n'); print('noise', flush=True); bench.emit({'ok': 1})"
+    proc = subprocess.run([sys.executable, "-c", code], cwd=str(ROOT), capture_output=True, text=True, timeout=120)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    assert proc.stdout.strip() == '{"ok": 1}'
+    assert "NCCL version" in proc.stderr and "noise" in proc.stderr
